@@ -1,0 +1,136 @@
+/*
+ * pipegcn_b200 -- C ABI of the B200-native PipeGCN hot path (libpipegcn_b200.so).
+ *
+ * The reference (GATECH-EIC/PipeGCN @ 73ab949) is pure Python; it has no FFI.  Its
+ * plug-in seam is a set of Python objects (helper/context.py:4-5, module/layer.py:8).
+ * These entry points are what a ctypes binding of those objects calls; each one
+ * names the reference code it replaces.  All pointers are raw device pointers
+ * unless stated otherwise, every call is asynchronous on `stream`
+ * (a cudaStream_t passed as void*), never synchronises the host, and returns 0 on
+ * success or a negative pg_status; pg_last_error() describes the last failure of
+ * the calling thread.  The caller owns all memory.
+ */
+#ifndef PIPEGCN_B200_H
+#define PIPEGCN_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PG_ABI_VERSION 1
+
+/* element types of activations / gradients */
+#define PG_F32  0
+#define PG_BF16 1
+
+enum pg_status {
+  PG_OK = 0,
+  PG_ERR_INVALID = -1,      /* bad argument (null pointer, misaligned, unsupported width) */
+  PG_ERR_CUDA = -2,         /* a CUDA runtime/driver call failed */
+  PG_ERR_UNSUPPORTED = -3,  /* not available on this device / build */
+  PG_ERR_TIMEOUT = -4       /* a halo flag did not arrive within the spin bound */
+};
+
+int pg_abi_version(void);
+const char* pg_last_error(void);
+/* writes sm major*10+minor, SM count and L2 bytes of `device`; needs a GPU */
+int pg_device_info(int device, int* sm_arch, int* sm_count, int64_t* l2_bytes);
+
+/* ------------------------------------------------------------------------------------------
+ * Adjacency of one partition in CSR form plus the split of its long rows.
+ * Forward: rows = destination (`_V`) nodes, columns = source (`_U`) ids  (layer.py:47-49).
+ * Backward: rows = source ids, columns = destinations (DGL gspmm backward on the reversed graph).
+ * Rows with more than seg_len entries are cut into segments of seg_len that different
+ * warps reduce into fp32 partials; a fix-up pass sums the partials in segment order, so the
+ * result does not depend on scheduling.
+ * ---------------------------------------------------------------------------------------- */
+typedef struct pg_csr {
+  const int32_t* indptr;        /* [n_rows + 1] */
+  const int32_t* indices;       /* [nnz] */
+  int32_t n_rows;
+  int32_t seg_len;              /* > 0 */
+  int32_t n_long;               /* rows longer than seg_len */
+  int32_t n_seg;                /* total segments of the long rows */
+  const int32_t* long_row;      /* [n_long] row id */
+  const int32_t* long_seg_ptr;  /* [n_long + 1] first segment of every long row */
+  const int32_t* seg_long;      /* [n_seg] index into long_row */
+} pg_csr;
+
+/*
+ * Neighbour aggregate:
+ *   out[r, 0:d] = ( sum_{e in row r} x[indices[e], 0:d] ) / row_div[r]  ( + out[r, 0:d] if r < acc_rows )
+ * x and out have element type `dtype`, sums are fp32.  ldx/ldo are row strides in elements.
+ * row_div (fp32, [n_rows]) may be NULL (no division).  scratch: fp32 [n_seg * d_pad] where
+ * d_pad = d rounded up to 8; may be NULL when n_seg == 0.
+ * Replaces graph['_E'].update_all(fn.copy_src, fn.sum) and `/ degs` at
+ * /root/reference/module/layer.py:47-50, and their autograd.
+ */
+int pg_aggregate(const pg_csr* g, const void* x, int64_t ldx, void* out, int64_t ldo, int32_t d, int dtype,
+                 const float* row_div, int32_t acc_rows, float* scratch, void* stream);
+
+/* out[r, 0:d] = x[r, 0:d] / row_div[r]   (gradient of `/ degs`, layer.py:50) */
+int pg_row_div(const void* x, int64_t ldx, void* out, int64_t ldo, int32_t n_rows, int32_t d, int dtype,
+               const float* row_div, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Halo exchange (feature_buffer.py:165-194).  One descriptor per message of a launch; the
+ * array lives in device memory and is built once by Buffer.init_buffer.
+ * A message copies n_rows rows of `src` (gathered through idx, or contiguous from src_row0)
+ * to `dst` -- normally peer memory mapped over NVLink.  With `ema` set the sender first
+ * updates its fp32 mirror  ema <- m*ema + (1-m)*row  (feature_buffer.py:189-191) and ships
+ * the smoothed row.  When the last CTA of a message has stored its rows it publishes `value`
+ * to *flag with system-scope release semantics.
+ * ---------------------------------------------------------------------------------------- */
+typedef struct pg_msg {
+  const int32_t* idx;      /* [n_rows] source row ids, or NULL */
+  int64_t src_row0;        /* first source row when idx == NULL */
+  int32_t n_rows;
+  int32_t cta_begin;       /* first CTA of this message inside the launch (filled by the host) */
+  void* dst;               /* destination of row 0 */
+  int64_t ld_dst;          /* elements */
+  float* ema;              /* [n_rows, ld_ema] fp32 sender-side EMA mirror, or NULL */
+  int64_t ld_ema;
+  uint32_t* flag;          /* flag word to publish (peer memory), or NULL */
+  uint32_t* counter;       /* local arrival counter of this message (self resetting) */
+} pg_msg;
+
+/* rows per CTA used by pg_halo_push when the host fills cta_begin */
+int pg_push_rows_per_cta(void);
+
+int pg_halo_push(const pg_msg* msgs, int32_t n_msgs, int32_t n_ctas, const void* src, int64_t ld_src, int32_t d,
+                 int dtype, float momentum, uint32_t value, void* stream);
+
+/*
+ * Block the stream until every flags[i] >= value (acquire, system scope).  A bounded spin:
+ * after `timeout_ms` the kernel stores PG_ERR_TIMEOUT to *status (device word, may be NULL)
+ * and returns, so a dead peer cannot hang the GPU (the reference hangs in gloo wait(),
+ * feature_buffer.py:184).
+ */
+int pg_halo_wait(const uint32_t* const* flags, int32_t n_flags, uint32_t value, int32_t timeout_ms,
+                 int32_t* status, void* stream);
+
+/*
+ * grad[urow[i], 0:d] += sum_k recv[usrc[k], 0:d]  for k in [uptr[i], uptr[i+1]), in that order
+ * (peers ascending), replacing the per-peer loop at feature_buffer.py:208-217.
+ */
+int pg_boundary_add(void* grad, int64_t ld_grad, const void* recv, int64_t ld_recv, int32_t d, int dtype,
+                    const int32_t* urow, const int32_t* uptr, const int32_t* usrc, int32_t n_urow, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Symmetric heap: device memory that peers map through CUDA IPC (host pointers out).
+ * ---------------------------------------------------------------------------------------- */
+#define PG_IPC_HANDLE_BYTES 64
+int pg_heap_alloc(size_t bytes, void** ptr);
+int pg_heap_free(void* ptr);
+int pg_ipc_export(void* ptr, unsigned char* handle);
+int pg_ipc_import(const unsigned char* handle, void** ptr);
+int pg_ipc_close(void* ptr);
+int pg_enable_peer_access(int peer_device);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PIPEGCN_B200_H */

@@ -14,18 +14,33 @@ from torch import nn
 
 
 class OracleGraph:
-    """Bipartite `_U` -> `_V` graph of one rank: 0/1 CSR `A [N_in, num_all]` and its transpose."""
+    """Bipartite `_U` -> `_V` graph of one rank: 0/1 CSR `A [N_in, num_all]` and its transpose (int64)."""
 
     def __init__(self, u: torch.Tensor, v: torch.Tensor, num_in: int, num_all: int):
         self.num_in, self.num_all = int(num_in), int(num_all)
-        ones = torch.ones(u.numel(), dtype=torch.float32)
-        import warnings
-        warnings.filterwarnings("ignore", message="Sparse")
-        self.A = torch.sparse_coo_tensor(torch.stack([v, u]), ones, (num_in, num_all)).coalesce().to_sparse_csr()
-        self.At = torch.sparse_coo_tensor(torch.stack([u, v]), ones, (num_all, num_in)).coalesce().to_sparse_csr()
+        self.A = _csr(v, u, self.num_in)
+        self.At = _csr(u, v, self.num_all)
 
     def num_nodes(self, ntype):
         return self.num_all if ntype == "_U" else self.num_in
+
+
+def _csr(rows, cols, n_rows):
+    order = torch.argsort(rows, stable=True)          # edge order inside a row = edge-list order
+    indptr = torch.zeros(n_rows + 1, dtype=torch.int64)
+    indptr[1:] = torch.cumsum(torch.bincount(rows, minlength=n_rows), 0)
+    return indptr.contiguous(), cols[order].to(torch.int64).contiguous()
+
+
+def spmm_sum(csr, x: torch.Tensor) -> torch.Tensor:
+    """out[r] = sum_{e in row r} x[indices[e]]  -- oracle/csrc/spmm.c (layer.py:47-49)."""
+    from .cbuild import lib
+    indptr, indices = csr
+    x = x.detach().contiguous().float()
+    out = torch.empty(indptr.numel() - 1, x.shape[1], dtype=torch.float32)
+    lib().oracle_spmm_sum_f32(indptr.data_ptr(), indices.data_ptr(), x.data_ptr(), out.data_ptr(),
+                              indptr.numel() - 1, x.shape[1])
+    return out
 
 
 class _CopySrcSum(torch.autograd.Function):
@@ -34,11 +49,11 @@ class _CopySrcSum(torch.autograd.Function):
     @staticmethod
     def forward(ctx, graph, feat):
         ctx.graph = graph
-        return torch.sparse.mm(graph.A, feat)
+        return spmm_sum(graph.A, feat)
 
     @staticmethod
     def backward(ctx, g):
-        return None, torch.sparse.mm(ctx.graph.At, g.contiguous())
+        return None, spmm_sum(ctx.graph.At, g)
 
 
 class OracleSageLayer(nn.Module):

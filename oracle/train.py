@@ -70,6 +70,7 @@ class RankTrace:
     epoch_time: List[float] = field(default_factory=list)
     comm_time: List[float] = field(default_factory=list)
     reduce_time: List[float] = field(default_factory=list)
+    wall: List[float] = field(default_factory=list)                 # every epoch, no exclusions
 
 
 def run_rank(rs: RankSetup, args: OracleArgs, fabric, init_state=None, keep_trace=True, feat=None) -> RankTrace:
@@ -114,6 +115,7 @@ def run_rank(rs: RankSetup, args: OracleArgs, fabric, init_state=None, keep_trac
             tr.epoch_time.append(time.time() - t0)
             tr.comm_time.append(timer.tot_time())
             tr.reduce_time.append(reduce_time)
+        tr.wall.append(time.time() - t0)
         timer.clear()
         tr.losses.append(float(loss.item()))
         if keep_trace:

@@ -1,0 +1,95 @@
+"""ctypes binding of libpipegcn_b200.so (include/pipegcn_b200.h).
+
+The hot path has no Python/torch fall-back: if the shared object is missing the
+import of any op raises.  `PG_LIB` may point at an alternative build.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from pathlib import Path
+
+PG_F32, PG_BF16 = 0, 1
+PG_OK, PG_ERR_INVALID, PG_ERR_CUDA, PG_ERR_UNSUPPORTED, PG_ERR_TIMEOUT = 0, -1, -2, -3, -4
+IPC_HANDLE_BYTES = 64
+
+_LIB_PATH = Path(os.environ.get("PG_LIB", Path(__file__).resolve().parent / "libpipegcn_b200.so"))
+
+
+class PgError(RuntimeError):
+    pass
+
+
+class pg_csr(C.Structure):
+    _fields_ = [("indptr", C.c_void_p), ("indices", C.c_void_p), ("n_rows", C.c_int32), ("seg_len", C.c_int32),
+                ("n_long", C.c_int32), ("n_seg", C.c_int32), ("long_row", C.c_void_p), ("long_seg_ptr", C.c_void_p),
+                ("seg_long", C.c_void_p)]
+
+
+class pg_msg(C.Structure):
+    _fields_ = [("idx", C.c_void_p), ("src_row0", C.c_int64), ("n_rows", C.c_int32), ("cta_begin", C.c_int32),
+                ("dst", C.c_void_p), ("ld_dst", C.c_int64), ("ema", C.c_void_p), ("ld_ema", C.c_int64),
+                ("flag", C.c_void_p), ("counter", C.c_void_p)]
+
+
+def _load():
+    if not _LIB_PATH.exists():
+        raise PgError(f"{_LIB_PATH} is missing: build it with `python -m pipegcn_b200.build` "
+                      f"(the hot path has no fall-back)")
+    lib = C.CDLL(str(_LIB_PATH))
+    vp, i32, i64, u32, f32 = C.c_void_p, C.c_int32, C.c_int64, C.c_uint32, C.c_float
+    sig = {
+        "pg_abi_version": (C.c_int, []),
+        "pg_last_error": (C.c_char_p, []),
+        "pg_device_info": (C.c_int, [C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(i64)]),
+        "pg_aggregate": (C.c_int, [C.POINTER(pg_csr), vp, i64, vp, i64, i32, C.c_int, vp, i32, vp, vp]),
+        "pg_row_div": (C.c_int, [vp, i64, vp, i64, i32, i32, C.c_int, vp, vp]),
+        "pg_push_rows_per_cta": (C.c_int, []),
+        "pg_halo_push": (C.c_int, [vp, i32, i32, vp, i64, i32, C.c_int, f32, u32, vp]),
+        "pg_halo_wait": (C.c_int, [vp, i32, u32, i32, vp, vp]),
+        "pg_boundary_add": (C.c_int, [vp, i64, vp, i64, i32, C.c_int, vp, vp, vp, i32, vp]),
+        "pg_heap_alloc": (C.c_int, [C.c_size_t, C.POINTER(vp)]),
+        "pg_heap_free": (C.c_int, [vp]),
+        "pg_ipc_export": (C.c_int, [vp, C.c_char_p]),
+        "pg_ipc_import": (C.c_int, [C.c_char_p, C.POINTER(vp)]),
+        "pg_ipc_close": (C.c_int, [vp]),
+        "pg_enable_peer_access": (C.c_int, [C.c_int]),
+    }
+    for name, (res, args) in sig.items():
+        fn = getattr(lib, name)
+        fn.restype, fn.argtypes = res, args
+    if lib.pg_abi_version() != 1:
+        raise PgError(f"ABI version mismatch: library {lib.pg_abi_version()}, binding 1")
+    return lib, tuple(sig)
+
+
+lib, EXPORTS = _load()
+
+
+def check(rc: int, what: str = ""):
+    if rc != PG_OK:
+        msg = lib.pg_last_error().decode(errors="replace")
+        raise PgError(f"{what or 'libpipegcn_b200'} failed ({rc}): {msg}")
+
+
+def dtype_code(dtype) -> int:
+    import torch
+    if dtype == torch.float32:
+        return PG_F32
+    if dtype == torch.bfloat16:
+        return PG_BF16
+    raise PgError(f"unsupported activation dtype {dtype}; the hot path runs in float32 or bfloat16")
+
+
+def stream_ptr():
+    import torch
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+# number of kernels launched through this binding (bench.py reports it as `gpu_launches`)
+LAUNCHES = 0
+
+
+def count(n: int = 1):
+    global LAUNCHES
+    LAUNCHES += n

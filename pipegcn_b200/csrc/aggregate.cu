@@ -1,0 +1,287 @@
+// CSR neighbour aggregate (SURVEY.md K6/K7 forward, K11 backward) for sm_100a.
+//
+//   out[r,:] = ( sum_{e in row r} x[indices[e],:] ) / row_div[r]  (+ out[r,:] if r < acc_rows)
+//
+// HBM/L2-bound gather: no tensor cores.  A group of G lanes owns one row (or one segment of a
+// long row) and walks its edge list; every lane keeps VPL vectors of VB bytes of the feature
+// row in fp32 accumulators, so a neighbour row is fetched with coalesced 16-byte loads
+// (one 512 B row of 256 bf16 = one load instruction of a full warp).  U neighbour rows are
+// in flight per group before they are accumulated.  Rows longer than seg_len are cut into
+// segments reduced by different groups into fp32 partials and summed in segment order by a
+// fix-up kernel: deterministic, no atomics.
+#include <algorithm>
+#include "common.cuh"
+
+namespace pg {
+
+template <typename T, int VB, int G, int VPL, int U>
+__global__ void __launch_bounds__(256)
+agg_kernel(pg_csr g, const T* __restrict__ x, int64_t ldx, T* __restrict__ out, int64_t ldo, int nvec,
+           const float* __restrict__ row_div, int acc_rows, float* __restrict__ scratch, int64_t lds) {
+  using P = Pack<T, VB>;
+  using Raw = typename P::Raw;
+  constexpr int V = P::V;
+  constexpr int GROUPS = 256 / G;
+  const int lane = threadIdx.x & 31;
+  const int lane_g = threadIdx.x % G;
+  const unsigned gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << (lane & ~(G - 1)));
+  const int64_t item = static_cast<int64_t>(blockIdx.x) * GROUPS + threadIdx.x / G;
+  const int64_t n_items = static_cast<int64_t>(g.n_rows) + g.n_seg;
+  if (item >= n_items) return;   // whole group leaves together
+
+  int row, beg, end, seg = -1;
+  if (item < g.n_rows) {
+    row = static_cast<int>(item);
+    beg = __ldg(g.indptr + row);
+    end = __ldg(g.indptr + row + 1);
+    if (end - beg > g.seg_len) return;   // long row: its segments do the work
+  } else {
+    seg = static_cast<int>(item - g.n_rows);
+    const int li = __ldg(g.seg_long + seg);
+    row = __ldg(g.long_row + li);
+    const int k = seg - __ldg(g.long_seg_ptr + li);
+    const int rb = __ldg(g.indptr + row), re = __ldg(g.indptr + row + 1);
+    beg = rb + k * g.seg_len;
+    end = min(re, beg + g.seg_len);
+  }
+
+  for (int c0 = 0; c0 < nvec; c0 += G * VPL) {
+    float acc[VPL][V];
+#pragma unroll
+    for (int j = 0; j < VPL; ++j)
+#pragma unroll
+      for (int i = 0; i < V; ++i) acc[j][i] = 0.f;
+    bool act[VPL];
+    int64_t off[VPL];
+#pragma unroll
+    for (int j = 0; j < VPL; ++j) {
+      const int vi = c0 + lane_g + j * G;
+      act[j] = vi < nvec;
+      off[j] = static_cast<int64_t>(vi) * V;
+    }
+
+    for (int e0 = beg; e0 < end; e0 += G) {
+      const int n = min(G, end - e0);
+      const int my = (lane_g < n) ? __ldg(g.indices + e0 + lane_g) : 0;
+      for (int k = 0; k < n; k += U) {
+        Raw v[U][VPL];
+        bool ok[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const int s = __shfl_sync(gmask, my, (k + u) % G, G);
+          ok[u] = (k + u) < n;
+          const T* rp = x + static_cast<int64_t>(s) * ldx;
+#pragma unroll
+          for (int j = 0; j < VPL; ++j)
+            if (ok[u] && act[j]) v[u][j] = ld_vec<VB>(rp + off[j]);
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          if (!ok[u]) continue;
+#pragma unroll
+          for (int j = 0; j < VPL; ++j) {
+            if (!act[j]) continue;
+            float f[V];
+            P::unpack(v[u][j], f);
+#pragma unroll
+            for (int i = 0; i < V; ++i) acc[j][i] += f[i];
+          }
+        }
+      }
+    }
+
+    if (seg >= 0) {
+      float* sp = scratch + static_cast<int64_t>(seg) * lds;
+#pragma unroll
+      for (int j = 0; j < VPL; ++j) {
+        if (!act[j]) continue;
+#pragma unroll
+        for (int i = 0; i < V; ++i) sp[off[j] + i] = acc[j][i];
+      }
+    } else {
+      const float dv = row_div ? __ldg(row_div + row) : 1.f;
+      T* op = out + static_cast<int64_t>(row) * ldo;
+#pragma unroll
+      for (int j = 0; j < VPL; ++j) {
+        if (!act[j]) continue;
+        float r[V];
+#pragma unroll
+        for (int i = 0; i < V; ++i) r[i] = row_div ? acc[j][i] / dv : acc[j][i];
+        if (row < acc_rows) {
+          float o[V];
+          P::unpack(*reinterpret_cast<const Raw*>(op + off[j]), o);
+#pragma unroll
+          for (int i = 0; i < V; ++i) r[i] += o[i];
+        }
+        st_vec<VB>(op + off[j], P::pack(r));
+      }
+    }
+  }
+}
+
+// sums the fp32 partials of every long row in segment order and writes the row
+template <typename T, int VB>
+__global__ void __launch_bounds__(256)
+agg_fixup_kernel(pg_csr g, T* __restrict__ out, int64_t ldo, int nvec, const float* __restrict__ row_div,
+                 int acc_rows, const float* __restrict__ scratch, int64_t lds) {
+  using P = Pack<T, VB>;
+  constexpr int V = P::V;
+  const int li = blockIdx.x;
+  const int row = g.long_row[li];
+  const int s0 = g.long_seg_ptr[li], s1 = g.long_seg_ptr[li + 1];
+  const float dv = row_div ? row_div[row] : 1.f;
+  T* op = out + static_cast<int64_t>(row) * ldo;
+  for (int vi = threadIdx.x; vi < nvec; vi += blockDim.x) {
+    float r[V];
+#pragma unroll
+    for (int i = 0; i < V; ++i) r[i] = 0.f;
+    for (int s = s0; s < s1; ++s) {
+      const float* sp = scratch + static_cast<int64_t>(s) * lds + static_cast<int64_t>(vi) * V;
+#pragma unroll
+      for (int i = 0; i < V; ++i) r[i] += sp[i];
+    }
+#pragma unroll
+    for (int i = 0; i < V; ++i) r[i] = row_div ? r[i] / dv : r[i];
+    if (row < acc_rows) {
+      float o[V];
+      P::unpack(*reinterpret_cast<const typename P::Raw*>(op + static_cast<int64_t>(vi) * V), o);
+#pragma unroll
+      for (int i = 0; i < V; ++i) r[i] += o[i];
+    }
+    st_vec<VB>(op + static_cast<int64_t>(vi) * V, P::pack(r));
+  }
+}
+
+template <typename T, int VB, int G, int VPL>
+static int launch_agg(const pg_csr& g, const T* x, int64_t ldx, T* out, int64_t ldo, int nvec,
+                      const float* row_div, int acc_rows, float* scratch, int64_t lds, cudaStream_t st) {
+  constexpr int U = (VPL >= 4) ? 2 : 4;
+  constexpr int GROUPS = 256 / G;
+  const int64_t n_items = static_cast<int64_t>(g.n_rows) + g.n_seg;
+  if (n_items > 0) {
+    const int64_t blocks = (n_items + GROUPS - 1) / GROUPS;
+    agg_kernel<T, VB, G, VPL, U><<<static_cast<unsigned>(blocks), 256, 0, st>>>(g, x, ldx, out, ldo, nvec, row_div,
+                                                                                acc_rows, scratch, lds);
+    PG_LAUNCH_CHECK();
+  }
+  if (g.n_long > 0) {
+    agg_fixup_kernel<T, VB><<<g.n_long, 256, 0, st>>>(g, out, ldo, nvec, row_div, acc_rows, scratch, lds);
+    PG_LAUNCH_CHECK();
+  }
+  return PG_OK;
+}
+
+template <typename T, int VB>
+static int dispatch_agg(const pg_csr& g, const T* x, int64_t ldx, T* out, int64_t ldo, int nvec,
+                        const float* row_div, int acc_rows, float* scratch, int64_t lds, cudaStream_t st) {
+#define PG_AGG(G_, VPL_) return launch_agg<T, VB, G_, VPL_>(g, x, ldx, out, ldo, nvec, row_div, acc_rows, scratch, lds, st)
+  if (nvec <= 4) PG_AGG(4, 1);
+  if (nvec <= 8) PG_AGG(8, 1);
+  if (nvec <= 16) PG_AGG(16, 1);
+  if (nvec <= 32) PG_AGG(32, 1);
+  if (nvec <= 64) PG_AGG(32, 2);
+  PG_AGG(32, 4);
+#undef PG_AGG
+}
+
+template <typename T>
+static int aggregate_t(const pg_csr& g, const void* x, int64_t ldx, void* out, int64_t ldo, int d,
+                       const float* row_div, int acc_rows, float* scratch, cudaStream_t st) {
+  const int es = sizeof(T);
+  int vb = min(vec_bytes(x, ldx, es), vec_bytes(out, ldo, es));
+  // a vector must not straddle two rows: either d is a multiple of the vector or both strides leave room
+  while (vb > es) {
+    const int v = vb / es;
+    const int64_t dp = round_up(d, v);
+    if (d % v == 0 || (dp <= ldx && dp <= ldo)) break;
+    vb >>= 1;
+  }
+  const int v = vb / es;
+  const int nvec = static_cast<int>(round_up(d, v) / v);
+  const int64_t lds = round_up(d, 8);
+  PG_REQUIRE(g.n_seg == 0 || scratch != nullptr, "pg_aggregate: scratch is NULL but the graph has %d long-row segments", g.n_seg);
+  const T* xp = static_cast<const T*>(x);
+  T* op = static_cast<T*>(out);
+  switch (vb) {
+    case 16: return dispatch_agg<T, 16>(g, xp, ldx, op, ldo, nvec, row_div, acc_rows, scratch, lds, st);
+    case 8: return dispatch_agg<T, 8>(g, xp, ldx, op, ldo, nvec, row_div, acc_rows, scratch, lds, st);
+    case 4: return dispatch_agg<T, 4>(g, xp, ldx, op, ldo, nvec, row_div, acc_rows, scratch, lds, st);
+    default:
+      set_error("pg_aggregate: rows must be at least 4-byte aligned (vector width %d)", vb);
+      return PG_ERR_INVALID;
+  }
+}
+
+template <typename T, int VB>
+__global__ void __launch_bounds__(256)
+row_div_kernel(const T* __restrict__ x, int64_t ldx, T* __restrict__ out, int64_t ldo, int n_rows, int nvec,
+               const float* __restrict__ row_div) {
+  using P = Pack<T, VB>;
+  constexpr int V = P::V;
+  const int64_t total = static_cast<int64_t>(n_rows) * nvec;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int r = static_cast<int>(i / nvec), vi = static_cast<int>(i % nvec);
+    float f[V];
+    P::unpack(ld_vec<VB>(x + static_cast<int64_t>(r) * ldx + static_cast<int64_t>(vi) * V), f);
+    const float dv = __ldg(row_div + r);
+#pragma unroll
+    for (int k = 0; k < V; ++k) f[k] = f[k] / dv;
+    st_vec<VB>(out + static_cast<int64_t>(r) * ldo + static_cast<int64_t>(vi) * V, P::pack(f));
+  }
+}
+
+template <typename T>
+static int row_div_t(const void* x, int64_t ldx, void* out, int64_t ldo, int n_rows, int d, const float* row_div,
+                     cudaStream_t st) {
+  const int es = sizeof(T);
+  int vb = min(vec_bytes(x, ldx, es), vec_bytes(out, ldo, es));
+  while (vb > es) {
+    const int v = vb / es;
+    const int64_t dp = round_up(d, v);
+    if (d % v == 0 || (dp <= ldx && dp <= ldo)) break;
+    vb >>= 1;
+  }
+  const int v = vb / es;
+  const int nvec = static_cast<int>(round_up(d, v) / v);
+  const int64_t total = static_cast<int64_t>(n_rows) * nvec;
+  if (total == 0) return PG_OK;
+  const unsigned blocks = static_cast<unsigned>(std::min<int64_t>((total + 255) / 256, 148 * 16));
+  const T* xp = static_cast<const T*>(x);
+  T* op = static_cast<T*>(out);
+  switch (vb) {
+    case 16: row_div_kernel<T, 16><<<blocks, 256, 0, st>>>(xp, ldx, op, ldo, n_rows, nvec, row_div); break;
+    case 8: row_div_kernel<T, 8><<<blocks, 256, 0, st>>>(xp, ldx, op, ldo, n_rows, nvec, row_div); break;
+    case 4: row_div_kernel<T, 4><<<blocks, 256, 0, st>>>(xp, ldx, op, ldo, n_rows, nvec, row_div); break;
+    default:
+      set_error("pg_row_div: rows must be at least 4-byte aligned");
+      return PG_ERR_INVALID;
+  }
+  PG_LAUNCH_CHECK();
+  return PG_OK;
+}
+
+}  // namespace pg
+
+extern "C" int pg_aggregate(const pg_csr* g, const void* x, int64_t ldx, void* out, int64_t ldo, int32_t d, int dtype,
+                            const float* row_div, int32_t acc_rows, float* scratch, void* stream) {
+  PG_REQUIRE(g && x && out, "pg_aggregate: null argument");
+  PG_REQUIRE(g->n_rows >= 0 && g->seg_len > 0 && d > 0, "pg_aggregate: bad sizes (n_rows=%d seg_len=%d d=%d)", g->n_rows, g->seg_len, d);
+  PG_REQUIRE(ldx >= d && ldo >= d, "pg_aggregate: row stride smaller than d");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (dtype == PG_F32) return pg::aggregate_t<float>(*g, x, ldx, out, ldo, d, row_div, acc_rows, scratch, st);
+  if (dtype == PG_BF16) return pg::aggregate_t<__nv_bfloat16>(*g, x, ldx, out, ldo, d, row_div, acc_rows, scratch, st);
+  pg::set_error("pg_aggregate: unknown dtype %d", dtype);
+  return PG_ERR_INVALID;
+}
+
+extern "C" int pg_row_div(const void* x, int64_t ldx, void* out, int64_t ldo, int32_t n_rows, int32_t d, int dtype,
+                          const float* row_div, void* stream) {
+  PG_REQUIRE(x && out && row_div, "pg_row_div: null argument");
+  PG_REQUIRE(n_rows >= 0 && d > 0 && ldx >= d && ldo >= d, "pg_row_div: bad sizes");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (dtype == PG_F32) return pg::row_div_t<float>(x, ldx, out, ldo, n_rows, d, row_div, st);
+  if (dtype == PG_BF16) return pg::row_div_t<__nv_bfloat16>(x, ldx, out, ldo, n_rows, d, row_div, st);
+  pg::set_error("pg_row_div: unknown dtype %d", dtype);
+  return PG_ERR_INVALID;
+}

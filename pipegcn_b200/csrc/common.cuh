@@ -1,0 +1,108 @@
+// Shared device/host helpers of libpipegcn_b200 (sm_100a only).
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/pipegcn_b200.h"
+
+namespace pg {
+
+void set_error(const char* fmt, ...);
+
+#define PG_CHECK_CUDA(expr)                                                              \
+  do {                                                                                   \
+    cudaError_t _e = (expr);                                                             \
+    if (_e != cudaSuccess) {                                                             \
+      pg::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+      return PG_ERR_CUDA;                                                                \
+    }                                                                                    \
+  } while (0)
+
+#define PG_REQUIRE(cond, ...)          \
+  do {                                 \
+    if (!(cond)) {                     \
+      pg::set_error(__VA_ARGS__);      \
+      return PG_ERR_INVALID;           \
+    }                                  \
+  } while (0)
+
+#define PG_LAUNCH_CHECK()                                                               \
+  do {                                                                                  \
+    cudaError_t _e = cudaGetLastError();                                                \
+    if (_e != cudaSuccess) {                                                            \
+      pg::set_error("kernel launch failed: %s (%s:%d)", cudaGetErrorString(_e), __FILE__, __LINE__); \
+      return PG_ERR_CUDA;                                                               \
+    }                                                                                   \
+  } while (0)
+
+// ---- raw vectors of VB bytes -------------------------------------------------------------
+template <int VB> struct RawVec;
+template <> struct RawVec<16> { using type = uint4; };
+template <> struct RawVec<8>  { using type = uint2; };
+template <> struct RawVec<4>  { using type = uint32_t; };
+template <> struct RawVec<2>  { using type = uint16_t; };
+
+// read-only gather path; rows are re-read by other CTAs, so keep them cacheable in L2/L1
+template <int VB>
+__device__ __forceinline__ typename RawVec<VB>::type ld_vec(const void* p) {
+  return __ldg(reinterpret_cast<const typename RawVec<VB>::type*>(p));
+}
+template <int VB>
+__device__ __forceinline__ void st_vec(void* p, typename RawVec<VB>::type v) {
+  *reinterpret_cast<typename RawVec<VB>::type*>(p) = v;
+}
+
+// ---- unpack VB bytes of T into floats / pack back ------------------------------------------
+template <typename T, int VB> struct Pack;
+
+template <int VB> struct Pack<float, VB> {
+  static constexpr int V = VB / 4;
+  using Raw = typename RawVec<VB>::type;
+  __device__ __forceinline__ static void unpack(const Raw& r, float* f) {
+    const float* p = reinterpret_cast<const float*>(&r);
+#pragma unroll
+    for (int i = 0; i < V; ++i) f[i] = p[i];
+  }
+  __device__ __forceinline__ static Raw pack(const float* f) {
+    Raw r;
+    float* p = reinterpret_cast<float*>(&r);
+#pragma unroll
+    for (int i = 0; i < V; ++i) p[i] = f[i];
+    return r;
+  }
+};
+
+template <int VB> struct Pack<__nv_bfloat16, VB> {
+  static constexpr int V = VB / 2;
+  using Raw = typename RawVec<VB>::type;
+  __device__ __forceinline__ static void unpack(const Raw& r, float* f) {
+    const uint16_t* p = reinterpret_cast<const uint16_t*>(&r);
+#pragma unroll
+    for (int i = 0; i < V; ++i) f[i] = __uint_as_float(static_cast<uint32_t>(p[i]) << 16);
+  }
+  __device__ __forceinline__ static Raw pack(const float* f) {
+    Raw r;
+    __nv_bfloat16* p = reinterpret_cast<__nv_bfloat16*>(&r);
+#pragma unroll
+    for (int i = 0; i < V; ++i) p[i] = __float2bfloat16_rn(f[i]);
+    return r;
+  }
+};
+
+__host__ __device__ inline int64_t round_up(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
+
+// largest power-of-two vector width (bytes, <= 16) that divides both the byte stride of a row
+// and the base address
+inline int vec_bytes(const void* base, int64_t ld_elems, int elem_bytes) {
+  uintptr_t a = reinterpret_cast<uintptr_t>(base);
+  int64_t stride = ld_elems * elem_bytes;
+  int vb = 16;
+  while (vb > elem_bytes && ((a % vb) != 0 || (stride % vb) != 0)) vb >>= 1;
+  return vb;
+}
+
+inline int elem_size(int dtype) { return dtype == PG_BF16 ? 2 : 4; }
+
+}  // namespace pg

@@ -1,0 +1,108 @@
+"""The graph object handed to the layers: CSR + CSC of one partition on the GPU.
+
+Takes the place of the DGL heterograph `('_U','_E','_V')` that
+/root/reference/train.py:`construct` builds (train.py:206-229) and
+/root/reference/module/layer.py:38-51 consumes; only `num_nodes('_U' | '_V')`
+and the adjacency survive.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional
+
+import torch
+
+from . import _C
+
+
+class CsrPlan:
+    """Device CSR + the split of its long rows, packaged as a `pg_csr` for the C ABI."""
+
+    def __init__(self, indptr: torch.Tensor, indices: torch.Tensor, seg_len: Optional[int] = None):
+        assert indptr.dtype == torch.int32 and indices.dtype == torch.int32
+        self.indptr, self.indices = indptr.contiguous(), indices.contiguous()
+        self.n_rows = int(indptr.numel() - 1)
+        self.nnz = int(indices.numel())
+        dev = indptr.device
+        deg = (self.indptr[1:] - self.indptr[:-1]).to(torch.int64)
+        if seg_len is None:
+            # segments of a few average rows: long enough to amortise the partial write,
+            # short enough that the heaviest hub is spread over hundreds of warps
+            mean = self.nnz / max(self.n_rows, 1)
+            seg_len = int(min(4096, max(256, 8 * mean)))
+        self.seg_len = int(seg_len)
+        long_mask = deg > self.seg_len
+        self.long_row = torch.nonzero(long_mask, as_tuple=True)[0].to(torch.int32)
+        n_long = int(self.long_row.numel())
+        nseg = (deg[long_mask] + self.seg_len - 1) // self.seg_len
+        self.long_seg_ptr = torch.zeros(n_long + 1, dtype=torch.int32, device=dev)
+        if n_long:
+            self.long_seg_ptr[1:] = torch.cumsum(nseg, 0).to(torch.int32)
+        self.n_seg = int(self.long_seg_ptr[-1].item()) if n_long else 0
+        self.seg_long = torch.repeat_interleave(torch.arange(n_long, dtype=torch.int32, device=dev), nseg) \
+            if n_long else torch.zeros(0, dtype=torch.int32, device=dev)
+        self.n_long = n_long
+        self.max_deg = int(deg.max().item()) if self.n_rows else 0
+        self._scratch = None
+        self.c = _C.pg_csr(self.indptr.data_ptr(), self.indices.data_ptr(), self.n_rows, self.seg_len, n_long,
+                           self.n_seg, self.long_row.data_ptr(), self.long_seg_ptr.data_ptr(),
+                           self.seg_long.data_ptr())
+
+    def scratch(self, d: int) -> Optional[torch.Tensor]:
+        if self.n_seg == 0:
+            return None
+        need = self.n_seg * ((d + 7) // 8 * 8)
+        if self._scratch is None or self._scratch.numel() < need:
+            self._scratch = torch.empty(need, dtype=torch.float32, device=self.indptr.device)
+        return self._scratch
+
+
+class PartGraph:
+    """Bipartite `_U` -> `_V` graph of one partition (forward CSR by `_V`, backward CSC by `_U`)."""
+
+    def __init__(self, num_in: int, num_all: int, indptr, indices, t_indptr, t_indices, in_deg,
+                 device="cuda", seg_len: Optional[int] = None):
+        self.num_in, self.num_all = int(num_in), int(num_all)
+        dev = torch.device(device)
+        self.fwd = CsrPlan(indptr.to(dev), indices.to(dev), seg_len)
+        self.bwd = CsrPlan(t_indptr.to(dev), t_indices.to(dev), seg_len)
+        self.in_deg = in_deg.to(dev)
+        self.in_deg_f = self.in_deg.to(torch.float32).contiguous()       # `/ degs` operand (layer.py:45,50)
+        self.device = dev
+
+    @classmethod
+    def from_layout(cls, lay, device="cuda", seg_len=None) -> "PartGraph":
+        return cls(lay.num_in, lay.num_all, lay.indptr, lay.indices, lay.t_indptr, lay.t_indices, lay.in_deg,
+                   device=device, seg_len=seg_len)
+
+    def deg_as_float(self, in_deg) -> torch.Tensor:
+        """fp32 view of the `in_deg` argument of GraphSAGELayer.forward (cached for the graph's own tensor)."""
+        if in_deg is None or in_deg is self.in_deg:
+            return self.in_deg_f
+        if in_deg.dtype == torch.float32 and in_deg.is_contiguous():
+            return in_deg
+        return in_deg.to(device=self.device, dtype=torch.float32).contiguous()
+
+    def row_degrees(self) -> torch.Tensor:
+        """`graph.in_degrees()` of the eval branch (layer.py:54): row lengths of the forward CSR."""
+        if not hasattr(self, "_row_deg_f"):
+            self._row_deg_f = (self.fwd.indptr[1:] - self.fwd.indptr[:-1]).to(torch.float32).contiguous()
+        return self._row_deg_f
+
+    def num_nodes(self, ntype: str = "_U") -> int:
+        if ntype == "_U":
+            return self.num_all
+        if ntype == "_V":
+            return self.num_in
+        raise KeyError(ntype)
+
+    @property
+    def nnz(self) -> int:
+        return self.fwd.nnz
+
+
+def alloc_rows(n_rows: int, d: int, dtype, device, zero: bool = False) -> torch.Tensor:
+    """[n_rows, d] view of storage whose row stride is padded to 8 elements (16-byte vectors)."""
+    ld = (d + 7) // 8 * 8
+    base = (torch.zeros if zero else torch.empty)(max(n_rows, 1), ld, dtype=dtype, device=device)
+    return base[:n_rows, :d]

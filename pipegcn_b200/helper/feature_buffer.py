@@ -1,0 +1,364 @@
+"""`Buffer`: the halo feature / gradient exchange of one rank, NVLink-native.
+
+Same public surface as /root/reference/helper/feature_buffer.py (`init_buffer`
+:45-46, `update` :143, `next_epoch` :129) with the data path replaced:
+
+reference                                             here
+---------------------------------------------------   ------------------------------------------
+gather rows -> pinned host -> gloo isend/irecv ->     one kernel gathers the boundary rows and
+pinned host -> H2D copy, one peer at a time           stores them straight into every peer's
+(:165-194), ThreadPool + side streams + events        `f_buf` halo rows over NVLink, then
+                                                      publishes a flag (pg_halo_push)
+torch.cat([feat] + recv buffers) (:132-141)           the peers write into rows [N_in:] of the
+                                                      [num_all, d] tensor `update` returns; only
+                                                      the inner rows are copied
+EMA on the receiver after the H2D copy (:186-191)     sender-side fp32 mirror, fused in the push
+                                                      kernel (same value sequence, same rounding)
+per-peer grad[boundary[i]] += recv (:208-217)         one ordered scatter-add kernel
+blocking r.wait() / event waits (:144-148,154-158)    a flag-wait kernel on the compute stream,
+                                                      bracketed by CUDA events (= exposed comm)
+
+Staleness (`pipeline=True`): the message produced at (epoch t, layer l) is consumed
+at (t+1, l); epoch 0 consumes zeros.  Two buffer versions (epoch parity) make this safe:
+the per-epoch gradient all-reduce separates a version's last read from its next write
+(SURVEY.md Appendix A.6).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import List, Optional
+
+import torch
+
+from .. import _C
+from ..world import Heap, default_world
+from .timer.timer import comm_timer
+
+_ALIGN = 256
+
+
+def _round_up(x: int, m: int) -> int:
+    return (x + m - 1) // m * m
+
+
+class _MsgSet:
+    """Device array of pg_msg for one launch."""
+
+    def __init__(self, msgs: List[_C.pg_msg], device):
+        rows_per_cta = _C.lib.pg_push_rows_per_cta()
+        cta = 0
+        for m in msgs:
+            m.cta_begin = cta
+            cta += (m.n_rows + rows_per_cta - 1) // rows_per_cta
+        self.n_msgs, self.n_ctas = len(msgs), cta
+        arr = (_C.pg_msg * len(msgs))(*msgs)
+        raw = bytes(arr)
+        self.dev = torch.frombuffer(bytearray(raw), dtype=torch.uint8).to(device)
+        self.ptr = self.dev.data_ptr()
+
+
+class _HaloUpdate(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, feat, buf, layer):
+        ctx.buf, ctx.layer, ctx.epoch = buf, layer, buf._epoch
+        return buf._forward(layer, feat)
+
+    @staticmethod
+    def backward(ctx, grad):
+        return ctx.buf._backward(ctx.layer, ctx.epoch, grad), None, None
+
+
+class Buffer(object):
+
+    def __init__(self, world=None):
+        super().__init__()
+        self._world = world
+        self._epoch = 0
+        self._ready = False
+        self._connected = False
+        self._pipeline = False
+        self.timeout_ms = 20000
+        self.timer = comm_timer
+
+    # ------------------------------------------------------------------ set-up
+    def init_buffer(self, num_in, num_all, boundary, f_recv_shape, layer_size, use_pp=False, backend='nccl',
+                    pipeline=False, corr_feat=False, corr_grad=False, corr_momentum=0,
+                    dtype=torch.float32, world=None):
+        if backend not in ('nccl', 'nvlink'):
+            # the reference implements gloo only and raises for the rest (feature_buffer.py:204-205);
+            # this engine implements the NVLink path only
+            raise NotImplementedError(f"backend '{backend}': only the NVLink/NCCL path exists in this engine")
+        if world is not None:
+            self._world = world
+        if self._world is None:
+            self._world = default_world()
+        w = self._world
+        rank, size = w.rank, w.size
+        dev = w.device
+        self._num_in, self._num_all = int(num_in), int(num_all)
+        self._boundary = boundary
+        self._n_layers = len(layer_size)
+        self._layer_size = list(layer_size)
+        self._pipeline = bool(pipeline)
+        self._epoch = 0
+        self._recv_shape = list(f_recv_shape)
+        self._corr_feat, self._corr_grad = bool(corr_feat), bool(corr_grad)
+        self._corr_momentum = float(corr_momentum)
+        self._use_pp = bool(use_pp)
+        self._dtype = dtype
+        self._es = torch.empty(0, dtype=dtype).element_size()
+        self._nver = 2 if pipeline else 1
+        self._peers = [j for j in range(size) if j != rank]
+        L = self._n_layers
+
+        # rows [pl[j], pr[j]) of the [num_all] space hold peer j's halo (feature_buffer.py:33-43)
+        self._pl, self._pr = [None] * size, [None] * size
+        tot = self._num_in
+        for j in range(size):
+            if j == rank:
+                continue
+            self._pl[j] = tot
+            tot += int(f_recv_shape[j])
+            self._pr[j] = tot
+        assert tot == self._num_all, f"recv shapes {f_recv_shape} do not add up to num_all={num_all}"
+
+        # concatenated boundary space: rows [boff[j], boff[j]+B_j) of b_recv belong to peer j
+        self._bidx = [None] * size
+        self._boff = [0] * size
+        btot = 0
+        for j in range(size):
+            if j == rank:
+                continue
+            self._boff[j] = btot
+            self._bidx[j] = boundary[j].to(device=dev, dtype=torch.int32).contiguous()
+            btot += int(boundary[j].numel())
+        self._btot = btot
+
+        # ---- carve the symmetric heap
+        self._ld = [_round_up(d, 8) for d in layer_size]
+        off = 0
+        self._flag_off = off
+        off = _round_up(off + 4 * L * 2 * size, _ALIGN)
+        self._f_off, self._b_off = {}, {}
+        for l in range(L):
+            if l == 0 and use_pp:
+                continue
+            for v in range(self._nver):
+                self._f_off[(l, v)] = off
+                off = _round_up(off + self._num_all * self._ld[l] * self._es, _ALIGN)
+                if l > 0:
+                    self._b_off[(l, v)] = off
+                    off = _round_up(off + max(btot, 1) * self._ld[l] * self._es, _ALIGN)
+        self._heap = Heap(max(off, _ALIGN), dev)
+        self._flags = self._heap.view(self._flag_off, (L, 2, size), torch.int32)
+        self._f_buf = {k: self._heap.view(o, (self._num_all, self._ld[k[0]]), dtype) for k, o in self._f_off.items()}
+        self._b_recv = {k: self._heap.view(o, (max(btot, 1), self._ld[k[0]]), dtype) for k, o in self._b_off.items()}
+
+        # ---- sender-side EMA mirrors (fp32), one per (layer, peer)
+        self._f_ema = [None] * L
+        self._b_ema = [None] * L
+        for l in range(L):
+            if l == 0 and use_pp:
+                continue
+            if corr_feat:
+                self._f_ema[l] = {j: torch.zeros(int(boundary[j].numel()), self._ld[l], device=dev) for j in self._peers}
+            if corr_grad and l > 0:
+                self._b_ema[l] = {j: torch.zeros(int(f_recv_shape[j]), self._ld[l], device=dev) for j in self._peers}
+
+        # ---- ordered boundary add: for every inner row that is a boundary row of some peer, the
+        #      rows of b_recv to add, peers ascending (feature_buffer.py:210-217)
+        if btot > 0:
+            rows = torch.cat([self._bidx[j].to(torch.int64) for j in self._peers])
+            slot = torch.arange(btot, device=dev, dtype=torch.int64)
+            order = torch.argsort(rows * btot + slot)          # by row, then by concatenated slot (= peer order)
+            rows_s = rows[order]
+            urow, counts = torch.unique_consecutive(rows_s, return_counts=True)
+            self._urow = urow.to(torch.int32).contiguous()
+            uptr = torch.zeros(urow.numel() + 1, dtype=torch.int64, device=dev)
+            uptr[1:] = torch.cumsum(counts, 0)
+            self._uptr = uptr.to(torch.int32).contiguous()
+            self._usrc = slot[order].to(torch.int32).contiguous()
+        else:
+            self._urow = self._uptr = self._usrc = None
+
+        self._counters = torch.zeros(max(1, 4 * L * size * self._nver), dtype=torch.int32, device=dev)
+        self._status = torch.zeros(1, dtype=torch.int32, device=dev)
+        self._comm_stream = torch.cuda.Stream(device=dev) if dev.type == 'cuda' else None
+        self._keep = []
+
+        w.publish('pipegcn.buffer', {
+            'heap': w.heap_token(self._heap), 'f_off': dict(self._f_off), 'b_off': dict(self._b_off),
+            'flag_off': self._flag_off, 'pl': list(self._pl), 'boff': list(self._boff), 'ld': list(self._ld),
+            'n_layers': L, 'nver': self._nver, 'es': self._es,
+        })
+        self._ready, self._connected = True, False
+
+    def _connect(self):
+        """Map the peers' heaps and build the message descriptors (needs every rank's table)."""
+        w = self._world
+        rank, size, dev = w.rank, w.size, w.device
+        tables = w.collect('pipegcn.buffer')
+        base = {j: w.map_peer(tables[j]['heap']) for j in range(size)}
+        L, es = self._n_layers, self._es
+        for j in self._peers:
+            t = tables[j]
+            if t['ld'] != self._ld or t['nver'] != self._nver or t['es'] != es:
+                raise RuntimeError(f"rank {j} was initialised with a different layer/dtype/pipeline configuration")
+        cnt = iter(range(self._counters.numel()))
+
+        def counter_ptr():
+            return self._counters.data_ptr() + 4 * next(cnt)
+
+        def flag_ptr(j, l, direction):
+            # word (l, direction, source=rank) of rank j's flag array
+            return base[j] + tables[j]['flag_off'] + 4 * ((l * 2 + direction) * size + rank)
+
+        self._self_msgs, self._fwd_msgs, self._bwd_msgs = {}, {}, {}
+        for (l, v) in self._f_off:
+            ld = self._ld[l]
+            m = _C.pg_msg(None, 0, self._num_in, 0, self._f_buf[(l, v)].data_ptr(), ld, None, 0, None, None)
+            self._self_msgs[(l, v)] = _MsgSet([m], dev)
+            msgs = []
+            for j in self._peers:
+                dst = base[j] + tables[j]['f_off'][(l, v)] + tables[j]['pl'][rank] * ld * es
+                ema = self._f_ema[l][j] if self._f_ema[l] is not None else None
+                msgs.append(_C.pg_msg(self._bidx[j].data_ptr(), 0, int(self._bidx[j].numel()), 0, dst, ld,
+                                      ema.data_ptr() if ema is not None else None, ld,
+                                      flag_ptr(j, l, 0), counter_ptr()))
+            self._fwd_msgs[(l, v)] = _MsgSet(msgs, dev) if msgs else None
+        for (l, v) in self._b_off:
+            ld = self._ld[l]
+            msgs = []
+            for j in self._peers:
+                dst = base[j] + tables[j]['b_off'][(l, v)] + tables[j]['boff'][rank] * ld * es
+                ema = self._b_ema[l][j] if self._b_ema[l] is not None else None
+                msgs.append(_C.pg_msg(None, self._pl[j], int(self._recv_shape[j]), 0, dst, ld,
+                                      ema.data_ptr() if ema is not None else None, ld,
+                                      flag_ptr(j, l, 1), counter_ptr()))
+            self._bwd_msgs[(l, v)] = _MsgSet(msgs, dev) if msgs else None
+        # device arrays of the flag words this rank waits on, per (layer, direction)
+        self._wait = {}
+        for l in range(L):
+            for direction in (0, 1):
+                ptrs = [self._heap.ptr + self._flag_off + 4 * ((l * 2 + direction) * size + j) for j in self._peers]
+                self._wait[(l, direction)] = torch.tensor(ptrs, dtype=torch.int64, device=dev) if ptrs else None
+        self._connected = True
+
+    # ------------------------------------------------------------------ epoch control
+    def next_epoch(self):
+        self._epoch += 1
+        self._keep.clear()
+
+    def check_status(self):
+        """Raises if a flag wait timed out since the last check (host sync)."""
+        if int(self._status.item()) != 0:
+            self._status.zero_()
+            raise _C.PgError("halo exchange: a peer's flag did not arrive within "
+                             f"{self.timeout_ms} ms (PG_ERR_TIMEOUT)")
+
+    # ------------------------------------------------------------------ kernels
+    def _push(self, ms: Optional[_MsgSet], src: torch.Tensor, d: int, value: int):
+        if ms is None:
+            return
+        _C.count(2)
+        _C.check(_C.lib.pg_halo_push(ms.ptr, ms.n_msgs, ms.n_ctas, src.data_ptr(), src.stride(0), d,
+                                     _C.dtype_code(src.dtype), self._corr_momentum, value & 0xffffffff,
+                                     _C.stream_ptr()), "pg_halo_push")
+
+    def _wait_flags(self, layer: int, direction: int, value: int, name: str):
+        ptrs = self._wait[(layer, direction)]
+        if ptrs is None:
+            return
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        _C.count()
+        _C.check(_C.lib.pg_halo_wait(ptrs.data_ptr(), ptrs.numel(), value & 0xffffffff, self.timeout_ms,
+                                     self._status.data_ptr(), _C.stream_ptr()), "pg_halo_wait")
+        e1.record()
+        self.timer.add_events(name, e0, e1)
+
+    def _check_feat(self, layer, feat):
+        if not self._ready:
+            raise RuntimeError("Buffer.update before init_buffer")
+        if feat.dim() != 2 or feat.shape[0] != self._num_in or feat.shape[1] != self._layer_size[layer]:
+            raise ValueError(f"update(layer={layer}): expected [{self._num_in}, {self._layer_size[layer]}], "
+                             f"got {tuple(feat.shape)}")
+        if feat.dtype != self._dtype:
+            raise TypeError(f"update(layer={layer}): buffer dtype is {self._dtype}, feat is {feat.dtype}")
+        if not feat.is_cuda:
+            raise _C.PgError("Buffer.update needs a CUDA tensor (no CPU fall-back)")
+
+    # ------------------------------------------------------------------ forward
+    def update(self, layer, feat):
+        """[N_in, d] -> [num_all, d] = cat(feat, halo rows of every peer); differentiable wrt feat."""
+        self._check_feat(layer, feat)
+        if not self._connected:
+            self._connect()
+        return _HaloUpdate.apply(feat, self, layer)
+
+    def _forward(self, layer, feat):
+        d = self._layer_size[layer]
+        t = self._epoch
+        if feat.stride(1) != 1:
+            feat = feat.contiguous()
+        if not self._pipeline:
+            v = 0
+            self._push(self._self_msgs[(layer, v)], feat, d, 0)
+            self._push(self._fwd_msgs[(layer, v)], feat, d, t + 1)
+            self._wait_flags(layer, 0, t + 1, f'forward_{layer}')
+        else:
+            v_use, v_send = (t + 1) % 2, t % 2
+            v = v_use
+            self._push(self._self_msgs[(layer, v_use)], feat, d, 0)
+            if t > 0:
+                self._wait_flags(layer, 0, t, f'forward_{layer}')
+            ms = self._fwd_msgs[(layer, v_send)]
+            if ms is not None:
+                cur = torch.cuda.current_stream()
+                self._comm_stream.wait_stream(cur)
+                feat.record_stream(self._comm_stream)
+                self._keep.append(feat)
+                with torch.cuda.stream(self._comm_stream):
+                    self._push(ms, feat, d, t + 1)
+        return self._f_buf[(layer, v)][:, :d]
+
+    # ------------------------------------------------------------------ backward
+    def _backward(self, layer, epoch, grad):
+        d = self._layer_size[layer]
+        t = epoch
+        if grad.stride(1) != 1:
+            grad = grad.contiguous()
+        if not self._pipeline:
+            v = 0
+            self._push(self._bwd_msgs[(layer, v)], grad, d, t + 1)
+            self._wait_flags(layer, 1, t + 1, f'backward_{layer}')
+            self._boundary_add(layer, v, grad)
+        else:
+            v_use, v_send = (t + 1) % 2, t % 2
+            if t > 0:
+                self._wait_flags(layer, 1, t, f'backward_{layer}')
+            self._boundary_add(layer, v_use, grad)
+            ms = self._bwd_msgs[(layer, v_send)]
+            if ms is not None:
+                cur = torch.cuda.current_stream()
+                self._comm_stream.wait_stream(cur)
+                grad.record_stream(self._comm_stream)
+                self._keep.append(grad)
+                with torch.cuda.stream(self._comm_stream):
+                    self._push(ms, grad, d, t + 1)
+        return grad[:self._num_in]
+
+    def _boundary_add(self, layer, v, grad):
+        if self._urow is None:
+            return
+        recv = self._b_recv[(layer, v)]
+        _C.count()
+        _C.check(_C.lib.pg_boundary_add(grad.data_ptr(), grad.stride(0), recv.data_ptr(), recv.stride(0),
+                                        self._layer_size[layer], _C.dtype_code(grad.dtype),
+                                        self._urow.data_ptr(), self._uptr.data_ptr(), self._usrc.data_ptr(),
+                                        int(self._urow.numel()), _C.stream_ptr()), "pg_boundary_add")
+
+    def synchronize(self):
+        """Join the side stream (end of training / before reading buffers on the host)."""
+        if self._comm_stream is not None:
+            torch.cuda.current_stream().wait_stream(self._comm_stream)

@@ -1,0 +1,85 @@
+"""`GraphSAGE` (alias `GCN`): the layer loop of /root/reference/module/model.py:25-58.
+
+Per graph layer: `buffer.update` (halo exchange) -> dropout -> GraphSAGELayer -> norm ->
+activation; trailing `n_linear` plain linears.  The reference defines no `GCN` class
+(SURVEY.md §0.2): the north-star's `module.model.GCN` is this class under a second name.
+state_dict keys match the reference (`layers.{i}.linear1.weight`, `norm.{i}.weight`, ...).
+
+Extra keyword arguments (not in the reference): `buffer` -- the exchange object to use
+instead of the process-global `helper.context.buffer` (several simulated ranks in one
+process); `dtype` -- activation storage type, float32 (reference) or bfloat16 (fp32
+accumulate, fp32 master weights).
+"""
+import torch
+from torch import nn
+import torch.nn.functional as F
+
+from ..helper import context as ctx
+from .layer import GraphSAGELayer
+
+
+class GNNBase(nn.Module):
+
+    def __init__(self, layer_size, activation, use_pp=False, dropout=0.5, norm='layer', n_linear=0):
+        super().__init__()
+        self.n_layers = len(layer_size) - 1
+        self.n_linear = n_linear
+        self.n_graph_layers = self.n_layers - n_linear
+        self.activation = activation
+        self.use_pp = use_pp
+        self.use_norm = norm is not None
+        self.layers = nn.ModuleList()
+        if self.use_norm:
+            self.norm = nn.ModuleList()
+        self.dropout = nn.Dropout(p=dropout)
+
+
+class GraphSAGE(GNNBase):
+
+    def __init__(self, layer_size, activation, use_pp, dropout=0.5, norm='layer', train_size=None, n_linear=0,
+                 buffer=None, dtype=torch.float32):
+        super().__init__(layer_size, activation, use_pp, dropout, norm, n_linear)
+        self.buffer = buffer
+        self.act_dtype = dtype
+        for i, (d_in, d_out) in enumerate(zip(layer_size[:-1], layer_size[1:])):
+            if i < self.n_graph_layers:
+                self.layers.append(GraphSAGELayer(d_in, d_out, use_pp=(use_pp and i == 0)))
+            else:
+                self.layers.append(nn.Linear(d_in, d_out))
+            if self.use_norm and i < self.n_layers - 1:
+                if norm == 'layer':
+                    self.norm.append(nn.LayerNorm(d_out, elementwise_affine=True))
+                elif norm == 'batch':
+                    from .sync_bn import SyncBatchNorm
+                    self.norm.append(SyncBatchNorm(d_out, train_size))
+                else:
+                    raise ValueError(f"unknown norm '{norm}'")
+
+    def _buffer(self):
+        return self.buffer if self.buffer is not None else ctx.buffer
+
+    def _norm_act(self, i, h):
+        if self.use_norm:
+            n = self.norm[i]
+            if isinstance(n, nn.LayerNorm) and h.dtype != n.weight.dtype:
+                h = F.layer_norm(h, n.normalized_shape, n.weight.to(h.dtype), n.bias.to(h.dtype), n.eps)
+            else:
+                h = n(h)
+        return self.activation(h)
+
+    def forward(self, g, feat, in_deg=None):
+        h = feat if feat.dtype == self.act_dtype else feat.to(self.act_dtype)
+        for i, layer in enumerate(self.layers):
+            if i < self.n_graph_layers:
+                if self.training and (i > 0 or not self.use_pp):
+                    h = self._buffer().update(i, h)
+                h = layer(g, self.dropout(h), in_deg)
+            else:
+                from .. import ops
+                h = ops.linear(self.dropout(h), layer.weight, layer.bias)
+            if i < self.n_layers - 1:
+                h = self._norm_act(i, h)
+        return h
+
+
+GCN = GraphSAGE

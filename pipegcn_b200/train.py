@@ -1,0 +1,207 @@
+"""Per-rank trainer: the epoch loop around the hot path.
+
+Keeps the entry points of /root/reference/train.py -- `init_processes(rank, size, args)`
+(:408-416) and `run(...)` (:242-400) -- and the order of an epoch (:341-362):
+forward, summed cross-entropy on the local train rows, backward (which runs the
+gradient halo exchange), `buffer.next_epoch()`, `reducer.synchronize()`, Adam step.
+The DGL partition arguments of the reference's `run(graph, node_dict, gpb, args)` are
+replaced by a `PartitionLayout` (pipegcn_b200/partition.py); evaluation and
+checkpointing are outside the hot path.
+
+`RankEngine` is one rank; `LocalTrainer` steps several simulated ranks of a
+`LocalWorld` in lock-step on one GPU (each on its own stream).
+"""
+from __future__ import annotations
+
+import os
+import time
+from typing import List, Optional
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+from .graph import PartGraph
+from .helper import context as ctx
+from .helper.feature_buffer import Buffer
+from .helper.reducer import Reducer
+from .helper.timer.comm_timer import CommTimer
+from .module.model import GraphSAGE
+from .partition import PartitionLayout, get_layer_size
+
+
+def create_model(layer_size, args, buffer=None, dtype=torch.float32):
+    if args.model in ('graphsage', 'gcn'):
+        return GraphSAGE(layer_size, F.relu, args.use_pp, norm=args.norm, dropout=args.dropout,
+                         n_linear=args.n_linear, train_size=args.n_train, buffer=buffer, dtype=dtype)
+    raise NotImplementedError(args.model)
+
+
+def reduce_hook(reducer, param, name, n_train):
+    def fn(grad):
+        reducer.reduce(param, name, grad, n_train)
+    return fn
+
+
+def act_dtype(args):
+    return torch.bfloat16 if getattr(args, 'dtype', 'fp32') in ('bf16', 'bfloat16') else torch.float32
+
+
+class RankEngine:
+    """Everything one rank owns: graph, exchange buffer, model replica, reducer, optimiser."""
+
+    def __init__(self, layout: PartitionLayout, args, world, buffer: Optional[Buffer] = None,
+                 reducer: Optional[Reducer] = None, init_state=None, seg_len=None):
+        self.args, self.world, self.rank = args, world, world.rank
+        dev = world.device
+        self.device = dev
+        self.dtype = act_dtype(args)
+        self.graph = PartGraph.from_layout(layout, device=dev, seg_len=seg_len)
+        self.in_deg = self.graph.in_deg
+        self.layer_size = get_layer_size(args.n_feat, args.n_hidden, args.n_class, args.n_layers)
+        self.buffer = buffer if buffer is not None else Buffer(world)
+        if buffer is None:
+            self.buffer.timer = CommTimer()
+        self.buffer.init_buffer(layout.num_in, layout.num_all, layout.boundary, layout.recv_shape,
+                                self.layer_size[:args.n_layers - args.n_linear], use_pp=args.use_pp,
+                                backend=args.backend, pipeline=args.enable_pipeline, corr_feat=args.feat_corr,
+                                corr_grad=args.grad_corr, corr_momentum=args.corr_momentum,
+                                dtype=self.dtype, world=world)
+        if args.use_pp:
+            raise NotImplementedError("--use-pp precompute is scheduled after the core path (SURVEY.md §8f-2)")
+        self.feat = layout.feat.to(dev).to(self.dtype)
+        tm = layout.train_mask.to(dev)
+        self.part_train = int(tm.sum().item())
+        prefix = bool(tm[:self.part_train].all().item()) if self.part_train else True
+        self.train_sel = slice(0, self.part_train) if prefix else tm
+        self.labels = layout.label.to(dev)[tm]
+        torch.manual_seed(args.seed)                                      # train.py:298
+        self.model = create_model(self.layer_size, args, buffer=self.buffer, dtype=self.dtype)
+        if init_state is not None:
+            self.model.load_state_dict(init_state)
+        self.model.to(dev)
+        self.reducer = reducer if reducer is not None else Reducer(world)
+        self.reducer.init(self.model, world)
+        for name, p in self.model.named_parameters():
+            p.register_hook(reduce_hook(self.reducer, p, name, args.n_train))
+        self.loss_fcn = torch.nn.CrossEntropyLoss(reduction='sum')        # train.py:320
+        self.optimizer = torch.optim.Adam(self.model.parameters(), lr=args.lr, weight_decay=args.weight_decay)
+        self.epoch = 0
+        self.last_logits = None
+
+    def forward_backward(self, keep_logits=False):
+        """train.py:343-355; returns the summed loss (device tensor, no host sync)."""
+        self.model.train()
+        logits = self.model(self.graph, self.feat, self.in_deg)
+        loss = self.loss_fcn(logits[self.train_sel].float(), self.labels)
+        if keep_logits:
+            self.last_logits = logits.detach()
+        self.optimizer.zero_grad(set_to_none=True)
+        loss.backward()
+        return loss.detach()
+
+    def finish_epoch(self, reduce=True):
+        """train.py:357-362."""
+        self.buffer.next_epoch()
+        if reduce:
+            self.reducer.synchronize()
+        self.optimizer.step()
+        self.epoch += 1
+
+    def run_epoch(self):
+        loss = self.forward_backward()
+        self.finish_epoch()
+        return loss
+
+
+class LocalTrainer:
+    """Lock-step driver of all ranks of a LocalWorld on one GPU (one stream per rank)."""
+
+    def __init__(self, layouts: List[PartitionLayout], args, local_world, init_state=None, seg_len=None):
+        self.world = local_world
+        self.engines = [RankEngine(l, args, local_world.view(r), init_state=init_state, seg_len=seg_len)
+                        for r, l in enumerate(layouts)]
+        self.streams = [torch.cuda.Stream(device=local_world.device) for _ in layouts]
+        for e in self.engines:
+            e.buffer.timeout_ms = 5000
+
+    def run_epoch(self, keep_logits=False):
+        cur = torch.cuda.current_stream()
+        losses = []
+        for e in self.engines:
+            e.buffer.timer.clear()
+        for e, s in zip(self.engines, self.streams):
+            s.wait_stream(cur)
+            with torch.cuda.stream(s):
+                losses.append(e.forward_backward(keep_logits))
+        for e, s in zip(self.engines, self.streams):
+            with torch.cuda.stream(s):
+                e.buffer.next_epoch()
+                e.reducer.pack()
+        for s in self.streams:
+            cur.wait_stream(s)
+        total = self.engines[0].reducer._flat.clone()
+        for e in self.engines[1:]:
+            total += e.reducer._flat
+        for e in self.engines:
+            e.reducer._flat.copy_(total)
+            e.reducer.unpack()
+            e.optimizer.step()
+            e.epoch += 1
+        for e in self.engines:
+            e.buffer.check_status()
+        return losses
+
+
+def run(layout: PartitionLayout, args, world=None):
+    """One rank's training loop with the reference's log line (train.py:341-375)."""
+    if world is None:
+        from .world import default_world
+        world = default_world()
+    rank = world.rank
+    engine = RankEngine(layout, args, world, buffer=ctx.buffer, reducer=ctx.reducer)
+    timer = engine.buffer.timer
+    train_dur, comm_dur, reduce_dur = [], [], []
+    for epoch in range(args.n_epochs):
+        torch.cuda.synchronize()
+        t0 = time.time()
+        loss = engine.forward_backward()
+        engine.buffer.next_epoch()
+        torch.cuda.synchronize()
+        pre_reduce = time.time()
+        engine.reducer.synchronize()
+        torch.cuda.synchronize()
+        reduce_time = time.time() - pre_reduce
+        engine.optimizer.step()
+        torch.cuda.synchronize()
+        if epoch >= 5 and epoch % args.log_every != 0:                    # train.py:364-367
+            train_dur.append(time.time() - t0)
+            comm_dur.append(timer.tot_time())
+            reduce_dur.append(reduce_time)
+        if (epoch + 1) % 10 == 0:
+            print("Process {:03d} | Epoch {:05d} | Time(s) {:.4f} | Comm(s) {:.4f} | Reduce(s) {:.4f} | Loss {:.4f}".format(
+                rank, epoch, np.mean(train_dur) if train_dur else float('nan'),
+                np.mean(comm_dur) if comm_dur else float('nan'),
+                np.mean(reduce_dur) if reduce_dur else float('nan'), loss.item() / max(engine.part_train, 1)))
+        timer.clear()
+        engine.buffer.check_status()
+    engine.buffer.synchronize()
+    return engine
+
+
+def check_parser(args):
+    if args.norm == 'none':
+        args.norm = None
+
+
+def init_processes(rank, size, args):
+    """Initialise the distributed environment and train this rank (train.py:408-416)."""
+    os.environ['MASTER_ADDR'] = args.master_addr
+    os.environ['MASTER_PORT'] = '%d' % args.port
+    import torch.distributed as dist
+    torch.cuda.set_device(rank % max(torch.cuda.device_count(), 1))
+    dist.init_process_group(args.backend, rank=rank, world_size=size)
+    check_parser(args)
+    from .helper.utils import load_partition
+    layout = load_partition(args, rank)
+    return run(layout, args)

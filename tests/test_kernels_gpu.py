@@ -1,0 +1,114 @@
+"""GPU parity of the individual kernels (through the C ABI) against plain fp32 torch on the host."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+DEV = "cuda"
+
+
+def _random_csr(n_rows, n_cols, avg_deg, seed, hubs=0, hub_deg=0):
+    g = torch.Generator().manual_seed(seed)
+    deg = torch.randint(0, 2 * avg_deg + 1, (n_rows,), generator=g)
+    for h in range(hubs):
+        deg[(h * 7919) % n_rows] = hub_deg
+    indptr = torch.zeros(n_rows + 1, dtype=torch.int64)
+    indptr[1:] = torch.cumsum(deg, 0)
+    indices = torch.randint(0, n_cols, (int(indptr[-1]),), generator=g)
+    return indptr.to(torch.int32), indices.to(torch.int32)
+
+
+def _ref_agg(indptr, indices, x, div=None):
+    n_rows = indptr.numel() - 1
+    rows = torch.repeat_interleave(torch.arange(n_rows), (indptr[1:] - indptr[:-1]).long())
+    out = torch.zeros(n_rows, x.shape[1], dtype=torch.float64)
+    out.index_add_(0, rows, x.double()[indices.long()])
+    if div is not None:
+        out = out / div.double()[:, None]
+    return out
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 2e-5), (torch.bfloat16, 1.6e-2)])
+@pytest.mark.parametrize("d", [1, 7, 16, 41, 64, 100, 128, 256, 602])
+def test_aggregate_matches_reference(dtype, tol, d):
+    from pipegcn_b200 import ops
+    from pipegcn_b200.graph import CsrPlan, alloc_rows
+    n_rows, n_cols = 3000, 5000
+    indptr, indices = _random_csr(n_rows, n_cols, 12, seed=d, hubs=3, hub_deg=2500)
+    plan = CsrPlan(indptr.to(DEV), indices.to(DEV), seg_len=512)
+    assert plan.n_long == 3 and plan.n_seg == 15
+    g = torch.Generator().manual_seed(d + 1)
+    x = torch.randn(n_cols, d, generator=g)
+    div = torch.randint(1, 50, (n_rows,), generator=g).float()
+    xd = alloc_rows(n_cols, d, dtype, DEV, zero=True)
+    xd.copy_(x.to(dtype))
+    out = ops.aggregate(plan, xd, row_div=div.to(DEV))
+    ref = _ref_agg(indptr, indices, xd.float().cpu(), div)
+    scale = ref.abs().max().item()
+    err = (out.float().cpu().double() - ref).abs().max().item()
+    assert err <= tol * scale + 1e-6, f"max err {err} scale {scale}"
+    # empty rows produce exact zeros
+    empty = (indptr[1:] == indptr[:-1]).nonzero().flatten()
+    assert empty.numel() > 0 and torch.count_nonzero(out[empty.to(DEV)]) == 0
+
+
+def test_aggregate_unpadded_and_accumulate():
+    """Contiguous (unpadded) fp32 input of odd width, plus the accumulate-into-rows mode of the backward."""
+    from pipegcn_b200 import ops
+    from pipegcn_b200.graph import CsrPlan
+    n_rows, n_cols, d = 500, 700, 37
+    indptr, indices = _random_csr(n_rows, n_cols, 9, seed=5)
+    plan = CsrPlan(indptr.to(DEV), indices.to(DEV), seg_len=256)
+    x = torch.randn(n_cols, d)
+    base = torch.randn(n_rows, d)
+    out = base.clone().to(DEV)
+    ops.aggregate(plan, x.to(DEV), out=out, acc_rows=300)
+    ref = _ref_agg(indptr, indices, x)
+    ref[:300] += base[:300].double()
+    torch.testing.assert_close(out.cpu().double(), ref, rtol=1e-5, atol=1e-5)
+
+
+def test_aggregate_deterministic_with_long_rows():
+    from pipegcn_b200 import ops
+    from pipegcn_b200.graph import CsrPlan
+    indptr, indices = _random_csr(2000, 2000, 20, seed=9, hubs=5, hub_deg=1900)
+    plan = CsrPlan(indptr.to(DEV), indices.to(DEV), seg_len=256)
+    x = torch.randn(2000, 256, device=DEV)
+    a = ops.aggregate(plan, x).clone()
+    b = ops.aggregate(plan, x).clone()
+    assert torch.equal(a, b)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_sage_aggregate_autograd_matches_oracle(dtype):
+    """Forward mean and backward A^T(g/deg) against the oracle's CPU autograd (oracle/model.py)."""
+    from oracle.model import OracleGraph, _CopySrcSum
+    from pipegcn_b200 import ops
+    from pipegcn_b200.graph import PartGraph
+    from tests.helpers import small_world
+    _, _, layouts, setups = small_world("tiny", 2)
+    L, S = layouts[1], setups[1]
+    graph = PartGraph.from_layout(L, device=DEV, seg_len=64)
+    d = 24
+    x = torch.randn(L.num_all, d)
+    go = torch.randn(L.num_in, d)
+    if dtype == torch.bfloat16:
+        x, go = x.bfloat16().float(), go.bfloat16().float()
+    xo = x.clone().requires_grad_(True)
+    og = OracleGraph(S.u, S.v, S.num_in, S.num_all)
+    ah_o = _CopySrcSum.apply(og, xo) / S.in_deg.unsqueeze(1)
+    ah_o.backward(go)
+    xg = x.to(DEV).to(dtype).requires_grad_(True)
+    ah = ops.sage_aggregate(xg, graph)
+    ah.backward(go.to(DEV).to(dtype))
+    tol = dict(rtol=1e-5, atol=1e-5) if dtype == torch.float32 else dict(rtol=2e-2, atol=2e-2)
+    torch.testing.assert_close(ah.float().cpu(), ah_o.detach(), **tol)
+    torch.testing.assert_close(xg.grad.float().cpu(), xo.grad, **tol)
+
+
+def test_row_div():
+    from pipegcn_b200 import ops
+    x = torch.randn(1000, 100, device=DEV)
+    div = torch.randint(1, 9, (1000,), device=DEV).float()
+    out = ops.row_div(x, div)
+    assert torch.equal(out, x / div[:, None])
