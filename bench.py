@@ -52,6 +52,7 @@ def parse():
     p.add_argument("--cpu-scale", type=int, default=16, help="CPU baseline runs on a 1/cpu-scale graph")
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--no-e2e", action="store_true")
+    p.add_argument("--ncu-region", action="store_true", help="cudaProfilerStart/Stop around the timed steps")
     return p.parse_args()
 
 
@@ -251,7 +252,11 @@ def main():
         comm_s.append(engine.buffer.timer)      # events resolved after the region
         engine.buffer.timer = type(engine.buffer.timer)()
 
+    if args.ncu_region:
+        torch.cuda.cudart().cudaProfilerStart()
     ms_total = timed(args.steps, step_prof)
+    if args.ncu_region:
+        torch.cuda.cudart().cudaProfilerStop()
     clocks = sampler.stop() if sampler else None
     launches = _C.LAUNCHES
     prof, ops.PROFILE = ops.PROFILE, None

@@ -75,6 +75,33 @@ int pg_aggregate(const pg_csr* g, const void* x, int64_t ldx, void* out, int64_t
 int pg_row_div(const void* x, int64_t ldx, void* out, int64_t ldo, int32_t n_rows, int32_t d, int dtype,
                const float* row_div, void* stream);
 
+/*
+ * Dense part of the layer on the tcgen05 tensor cores:
+ *   c[m, n] = sum_s a_s[m, k_s] * b_s[n, k_s]^T  (+ bias[n])  (/ row_div[m])      1 <= n_src <= 6
+ * dtype_in PG_BF16 -> kind::f16 MMA, PG_F32 -> kind::tf32 MMA; fp32 accumulation in TMEM;
+ * dtype_out selects the element type of c.  n <= 256.  All operands row-major with 16-byte
+ * aligned rows (TMA); k tails and the m tail are zero-filled / masked.  `srcs` is a HOST array.
+ * Replaces `self.linear1(feat[0:num_dst]) + self.linear2(ah)` at
+ * /root/reference/module/layer.py:51 (two pairs: inner rows x W1, neighbour mean x W2,
+ * bias = b1 + b2) and, with one pair, the dX products of its autograd (row_div = in_deg fuses the
+ * `/ degs` gradient).  fp32 parity mode passes the hi/lo halves of pg_split_tf32 as three pairs
+ * per product (hi*hi + hi*lo + lo*hi: the "3xTF32" product, fp32-grade accuracy).
+ */
+typedef struct pg_gemm_src {
+  const void* a;   /* [m, k] */
+  int64_t lda;
+  const void* b;   /* [n, k] */
+  int64_t ldb;
+  int32_t k;
+} pg_gemm_src;
+
+int pg_linear(int dtype_in, int dtype_out, const pg_gemm_src* srcs, int32_t n_src, const float* bias,
+              const float* row_div, void* c, int64_t ldc, int32_t m, int32_t n, void* stream);
+
+/* hi = x with the 13 low mantissa bits cleared (a tf32 value), lo = x - hi (exact); [rows, d] fp32 */
+int pg_split_tf32(const float* x, int64_t ldx, float* hi, float* lo, int64_t ld, int32_t rows, int32_t d,
+                  void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * Halo exchange (feature_buffer.py:165-194).  One descriptor per message of a launch; the
  * array lives in device memory and is built once by Buffer.init_buffer.

@@ -27,6 +27,7 @@ class OracleBuffer:
         self.fabric, self.rank, self.size = fabric, rank, size
         self.timer = timer
         self._epoch = 0
+        self.grad_trace = None     # when a dict: (epoch, layer) -> (grad handed to the hook, grad it returns)
 
     # feature_buffer.py:33-43
     def _init_pl_pr(self):
@@ -131,7 +132,10 @@ class OracleBuffer:
         L = self._n_layers
 
         def fn(grad):
+            g_in = grad.clone() if self.grad_trace is not None else None
             grad = grad.clone()       # autograd may hand out a shared buffer; the reference mutates in place
+            if g_in is not None:
+                self.grad_trace[(epoch, layer)] = (g_in, grad)   # `grad` is updated in place below
             if not self._pipeline:
                 with self._timed(f"backward_{layer}"):
                     tag = epoch * 2 * L + layer + L                          # :240

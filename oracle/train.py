@@ -71,6 +71,7 @@ class RankTrace:
     comm_time: List[float] = field(default_factory=list)
     reduce_time: List[float] = field(default_factory=list)
     wall: List[float] = field(default_factory=list)                 # every epoch, no exclusions
+    hook_grads: Dict = field(default_factory=dict)                  # (epoch, layer) -> (grad in, grad out) of the halo hook
 
 
 def run_rank(rs: RankSetup, args: OracleArgs, fabric, init_state=None, keep_trace=True, feat=None) -> RankTrace:
@@ -95,6 +96,8 @@ def run_rank(rs: RankSetup, args: OracleArgs, fabric, init_state=None, keep_trac
     loss_fcn = torch.nn.CrossEntropyLoss(reduction="sum")                 # train.py:320
     opt = torch.optim.Adam(model.parameters(), lr=args.lr, weight_decay=args.weight_decay)
     tr = RankTrace()
+    if keep_trace:
+        buf.grad_trace = tr.hook_grads
     for epoch in range(args.n_epochs):
         t0 = time.time()
         model.train()

@@ -26,6 +26,10 @@ class pg_csr(C.Structure):
                 ("seg_long", C.c_void_p)]
 
 
+class pg_gemm_src(C.Structure):
+    _fields_ = [("a", C.c_void_p), ("lda", C.c_int64), ("b", C.c_void_p), ("ldb", C.c_int64), ("k", C.c_int32)]
+
+
 class pg_msg(C.Structure):
     _fields_ = [("idx", C.c_void_p), ("src_row0", C.c_int64), ("n_rows", C.c_int32), ("cta_begin", C.c_int32),
                 ("dst", C.c_void_p), ("ld_dst", C.c_int64), ("ema", C.c_void_p), ("ld_ema", C.c_int64),
@@ -44,6 +48,8 @@ def _load():
         "pg_device_info": (C.c_int, [C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(i64)]),
         "pg_aggregate": (C.c_int, [C.POINTER(pg_csr), vp, i64, vp, i64, i32, C.c_int, vp, i32, vp, vp]),
         "pg_row_div": (C.c_int, [vp, i64, vp, i64, i32, i32, C.c_int, vp, vp]),
+        "pg_linear": (C.c_int, [C.c_int, C.c_int, C.POINTER(pg_gemm_src), i32, vp, vp, vp, i64, i32, i32, vp]),
+        "pg_split_tf32": (C.c_int, [vp, i64, vp, vp, i64, i32, i32, vp]),
         "pg_push_rows_per_cta": (C.c_int, []),
         "pg_halo_push": (C.c_int, [vp, i32, i32, vp, i64, i32, C.c_int, f32, u32, vp]),
         "pg_halo_wait": (C.c_int, [vp, i32, u32, i32, vp, vp]),

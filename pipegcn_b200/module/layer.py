@@ -45,10 +45,8 @@ class GraphSAGELayer(nn.Module):
         if self.training:
             if self.use_pp:
                 return ops.linear(feat, self.linear.weight, self.linear.bias)
-            num_dst = graph.num_nodes('_V')
-            ah = ops.sage_aggregate(feat, graph, graph.deg_as_float(in_deg))
-            return ops.sage_linear(feat[0:num_dst], ah, self.linear1.weight, self.linear1.bias,
-                                   self.linear2.weight, self.linear2.bias)
+            return ops.sage_layer(feat, graph, graph.deg_as_float(in_deg), self.linear1.weight, self.linear1.bias,
+                                  self.linear2.weight, self.linear2.bias)
         assert in_deg is None
         ah = ops.sage_aggregate(feat, graph, graph.row_degrees())
         if self.use_pp:

@@ -7,6 +7,7 @@ the aggregate / exchange path.
 from __future__ import annotations
 
 import ctypes as C
+import os
 
 import torch
 
@@ -49,7 +50,6 @@ def aggregate(plan: CsrPlan, x: torch.Tensor, out: torch.Tensor = None, row_div:
 
 # when a list, every aggregate launch appends (start event, end event, algorithmic bytes)
 PROFILE = None
-LINEAR_IMPL = "cublas (torch.nn.functional.linear); tcgen05 kernel pending"
 
 
 def aggregate_bytes(plan: CsrPlan, x: torch.Tensor, has_div: bool) -> int:
@@ -93,14 +93,174 @@ def sage_aggregate(feat: torch.Tensor, graph: PartGraph, deg_f: torch.Tensor = N
     return SageAggregate.apply(feat, graph, graph.in_deg_f if deg_f is None else deg_f)
 
 
-# ---- dense part.  Round-1 bring-up: library GEMM (cuBLAS through torch); the tcgen05 kernel
-# ---- (csrc/linear_tcgen05.cu) replaces it behind the same two functions.
+# ---- dense part: hand-written tcgen05 GEMM (csrc/linear_tcgen05.cu) -----------------------------
+LINEAR_IMPL = "tcgen05 (pg_linear: TMA + tcgen05.mma kind::f16 / 3xTF32, TMEM accumulators); dW via cuBLAS"
+
+
+def _tma_ready(t: torch.Tensor) -> torch.Tensor:
+    """Row-major view whose rows start on 16-byte boundaries (what a TMA descriptor needs)."""
+    if t.dim() == 2 and t.stride(1) == 1 and (t.stride(0) * t.element_size()) % 16 == 0 \
+            and t.data_ptr() % 16 == 0 and t.stride(0) >= t.shape[1]:
+        return t
+    out = alloc_rows(t.shape[0], t.shape[1], t.dtype, t.device)
+    out.copy_(t)
+    return out
+
+
+def padded_weight(w: torch.Tensor, dtype, transpose: bool = False) -> torch.Tensor:
+    """[n, k] copy of a weight (or of its transpose) in the activation dtype with 16-byte aligned rows."""
+    src = w.detach().t() if transpose else w.detach()
+    out = alloc_rows(src.shape[0], src.shape[1], dtype, w.device)
+    out.copy_(src)
+    return out
+
+
+def split_tf32(x: torch.Tensor):
+    """(hi, lo) with hi = x truncated to tf32 and lo = x - hi, both padded row-major fp32 (pg_split_tf32)."""
+    _rows(x)
+    hi = alloc_rows(x.shape[0], x.shape[1], torch.float32, x.device)
+    lo = alloc_rows(x.shape[0], x.shape[1], torch.float32, x.device)
+    if x.shape[0]:
+        _C.count()
+        _C.check(_C.lib.pg_split_tf32(x.data_ptr(), x.stride(0), hi.data_ptr(), lo.data_ptr(), hi.stride(0),
+                                      x.shape[0], x.shape[1], _C.stream_ptr()), "pg_split_tf32")
+    return hi, lo
+
+
+# fp32 activations: "3xtf32" = hi*hi + hi*lo + lo*hi on the tf32 tensor cores (fp32-grade accuracy, the
+# parity mode); "tf32" = one pass (rel. error ~1e-3).  bf16 activations always use one kind::f16 pass.
+FP32_GEMM = os.environ.get("PG_FP32_GEMM", "3xtf32")
+
+
+def gemm_nt(a0, b0, a1=None, b1=None, bias=None, row_div=None, out=None, out_dtype=None) -> torch.Tensor:
+    """out[m, n] = a0 @ b0^T (+ a1 @ b1^T) (+ bias) (/ row_div[:, None]) on the tcgen05 tensor cores."""
+    pairs = [(_rows(a0), _rows(b0))]
+    if a1 is not None:
+        pairs.append((_rows(a1), _rows(b1)))
+    m, n = a0.shape[0], b0.shape[0]
+    for a, b in pairs:
+        assert a.shape[0] == m and b.shape[0] == n and a.shape[1] == b.shape[1] and a.dtype == b.dtype == a0.dtype
+    if n > 256:
+        # one N tile holds at most 256 columns: split the weight rows
+        outs = [gemm_nt(a0, b0[i:i + 256], a1, None if b1 is None else b1[i:i + 256],
+                        None if bias is None else bias[i:i + 256], row_div, None, out_dtype)
+                for i in range(0, n, 256)]
+        res = torch.cat(outs, dim=1)
+        if out is not None:
+            out.copy_(res)
+            return out
+        return res
+    if out is None:
+        out = alloc_rows(m, n, out_dtype or a0.dtype, a0.device)
+    assert out.shape == (m, n) and out.stride(1) == 1
+    if m == 0:
+        return out
+    if a0.dtype == torch.float32 and FP32_GEMM == "3xtf32":
+        split = []
+        for a, b in pairs:
+            (ah, al), (bh, bl) = split_tf32(a), split_tf32(b)
+            split += [(ah, bh), (ah, bl), (al, bh)]
+        pairs = split
+    else:
+        pairs = [(_tma_ready(a), _tma_ready(b)) for a, b in pairs]
+    srcs = (_C.pg_gemm_src * len(pairs))(*[_C.pg_gemm_src(a.data_ptr(), a.stride(0), b.data_ptr(), b.stride(0),
+                                                            a.shape[1]) for a, b in pairs])
+    if bias is not None:
+        bias = bias.detach().to(torch.float32).contiguous()
+    _C.count()
+    _C.check(_C.lib.pg_linear(_C.dtype_code(a0.dtype), _C.dtype_code(out.dtype), srcs, len(pairs),
+                              bias.data_ptr() if bias is not None else None,
+                              row_div.data_ptr() if row_div is not None else None,
+                              out.data_ptr(), out.stride(0), m, n, _C.stream_ptr()), "pg_linear")
+    return out
+
+
+def _mm_f32(a_t: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
+    """a_t^T-shaped weight gradient  g^T @ x  with fp32 output (library GEMM: a plain cuBLAS call)."""
+    if a_t.dtype == torch.float32:
+        return torch.mm(a_t, b)
+    try:
+        return torch.mm(a_t, b, out_dtype=torch.float32)
+    except (TypeError, RuntimeError):
+        return torch.mm(a_t.float(), b.float())
+
+
+class _Linear(torch.autograd.Function):
+    """y = x @ W^T + b   (plain `nn.Linear` layers: use_pp layer 0 and the trailing n_linear layers)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias):
+        wp = padded_weight(weight, x.dtype)
+        ctx.save_for_backward(x, weight)
+        ctx.has_bias = bias is not None
+        return gemm_nt(x, wp, bias=bias)
+
+    @staticmethod
+    def backward(ctx, g):
+        x, weight = ctx.saved_tensors
+        g = _tma_ready(g if g.dtype == x.dtype else g.to(x.dtype))
+        gx = gemm_nt(g, padded_weight(weight, x.dtype, transpose=True)) if ctx.needs_input_grad[0] else None
+        gw = _mm_f32(g.t(), x).to(weight.dtype)
+        gb = g.float().sum(0) if ctx.has_bias else None
+        return gx, gw, gb
+
+
 def linear(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor = None) -> torch.Tensor:
-    w = weight if weight.dtype == x.dtype else weight.to(x.dtype)
-    b = bias if bias is None or bias.dtype == x.dtype else bias.to(x.dtype)
-    return torch.nn.functional.linear(x, w, b)
+    return _Linear.apply(x, weight, bias)
+
+
+class SageLayerFn(torch.autograd.Function):
+    """The whole training branch of GraphSAGELayer.forward (layer.py:44-51) and its gradient:
+
+        ah  = (A @ feat) / in_deg                         pg_aggregate
+        out = feat[:N_in] @ W1^T + ah @ W2^T + (b1 + b2)  pg_linear, two sources, one kernel
+
+        g_feat[:N_in] = g @ W1                            pg_linear
+        gs            = (g @ W2) / in_deg                 pg_linear with the row scale fused
+        g_feat       += A^T @ gs                          pg_aggregate accumulating into rows < N_in
+        gW1 = g^T feat[:N_in], gW2 = g^T ah, gb = sum g   library GEMM / reduction
+    """
+
+    @staticmethod
+    def forward(ctx, feat, graph, deg_f, w1, b1, w2, b2):
+        if feat.stride(1) != 1:
+            feat = feat.contiguous()
+        n_in = graph.num_in
+        ah = aggregate(graph.fwd, feat, row_div=deg_f)
+        x = feat[:n_in]
+        bias = None
+        if b1 is not None:
+            bias = b1.detach().float() + b2.detach().float()
+        out = gemm_nt(x, padded_weight(w1, feat.dtype), ah, padded_weight(w2, feat.dtype), bias=bias)
+        ctx.graph, ctx.deg_f = graph, deg_f
+        ctx.has_bias = b1 is not None
+        ctx.save_for_backward(x, ah, w1, w2)
+        ctx.num_all = feat.shape[0]
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        x, ah, w1, w2 = ctx.saved_tensors
+        graph, deg_f = ctx.graph, ctx.deg_f
+        g = _tma_ready(g if g.dtype == x.dtype else g.to(x.dtype))
+        g_feat = None
+        if ctx.needs_input_grad[0]:
+            d_in = x.shape[1]
+            g_feat = alloc_rows(ctx.num_all, d_in, x.dtype, x.device)
+            gemm_nt(g, padded_weight(w1, x.dtype, transpose=True), out=g_feat[:graph.num_in])
+            gs = gemm_nt(g, padded_weight(w2, x.dtype, transpose=True), row_div=deg_f)
+            aggregate(graph.bwd, gs, out=g_feat, acc_rows=graph.num_in)
+        gt = g.t()
+        gw1 = _mm_f32(gt, x).to(w1.dtype)
+        gw2 = _mm_f32(gt, ah).to(w2.dtype)
+        gb = g.float().sum(0) if ctx.has_bias else None
+        return g_feat, None, None, gw1, gb, gw2, gb
+
+
+def sage_layer(feat, graph, deg_f, w1, b1, w2, b2) -> torch.Tensor:
+    return SageLayerFn.apply(feat, graph, deg_f, w1, b1, w2, b2)
 
 
 def sage_linear(x, ah, w1, b1, w2, b2) -> torch.Tensor:
-    """x @ W1^T + b1 + ah @ W2^T + b2   (layer.py:51)."""
+    """x @ W1^T + b1 + ah @ W2^T + b2   (layer.py:51) -- un-fused composition (eval branch)."""
     return linear(x, w1, b1) + linear(ah, w2, b2)

@@ -118,12 +118,37 @@ class LocalTrainer:
     """Lock-step driver of all ranks of a LocalWorld on one GPU (one stream per rank)."""
 
     def __init__(self, layouts: List[PartitionLayout], args, local_world, init_state=None, seg_len=None):
+        self.streams = [torch.cuda.Stream(device=local_world.device) for _ in layouts]
+        if len(layouts) > 1 and not args.enable_pipeline:
+            self._dry_run(layouts, args, local_world, seg_len)
         self.world = local_world
         self.engines = [RankEngine(l, args, local_world.view(r), init_state=init_state, seg_len=seg_len)
                         for r, l in enumerate(layouts)]
-        self.streams = [torch.cuda.Stream(device=local_world.device) for _ in layouts]
         for e in self.engines:
             e.buffer.timeout_ms = 5000
+
+    def _dry_run(self, layouts, args, local_world, seg_len):
+        """One GPU, one process, non-pipelined exchange: a rank's flag-wait kernel spins until its peers'
+        pushes are LAUNCHED by this same host thread, so nothing on the host may synchronise with the
+        device in between (lazy module loading, first-use handle creation, allocator growth).  Two
+        throw-away pipelined epochs (which never wait on unlaunched work) on the same streams trigger
+        all of that first.  Real multi-GPU runs (one process per GPU) do not need this."""
+        import copy
+        from .world import LocalWorld
+        dry_args = copy.copy(args)
+        dry_args.enable_pipeline = True
+        dry = LocalTrainer.__new__(LocalTrainer)
+        dry.world = LocalWorld(local_world.size, local_world.device)
+        dry.streams = self.streams
+        dry.engines = [RankEngine(l, dry_args, dry.world.view(r), seg_len=seg_len) for r, l in enumerate(layouts)]
+        rng = torch.cuda.get_rng_state(local_world.device)
+        for _ in range(2):
+            dry.run_epoch()
+        torch.cuda.synchronize()
+        for e in dry.engines:
+            e.buffer._heap.free()
+        torch.cuda.set_rng_state(rng, local_world.device)
+        del dry
 
     def run_epoch(self, keep_logits=False):
         cur = torch.cuda.current_stream()

@@ -112,3 +112,66 @@ def test_row_div():
     div = torch.randint(1, 9, (1000,), device=DEV).float()
     out = ops.row_div(x, div)
     assert torch.equal(out, x / div[:, None])
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.bfloat16, 1e-2), (torch.float32, 2e-5)])
+@pytest.mark.parametrize("m,n,k0,k1", [(1000, 256, 256, 256), (4097, 256, 602, 0), (300, 41, 256, 256),
+                                       (128, 16, 20, 20), (77, 128, 100, 100), (5000, 64, 64, 0)])
+def test_linear_tcgen05(dtype, tol, m, n, k0, k1):
+    """pg_linear (tcgen05/TMEM/TMA) vs fp64 matmul of the same (rounded) inputs; bf16: rel 1e-2 (bf16 output
+    rounding), fp32 through the 3xTF32 product: rel 2e-5."""
+    from pipegcn_b200 import ops
+    from pipegcn_b200.graph import alloc_rows
+    g = torch.Generator().manual_seed(m + n)
+    def mk(r, c):
+        t = alloc_rows(r, c, dtype, DEV, zero=True)
+        t.copy_(torch.randn(r, c, generator=g).to(dtype))
+        return t
+    a0, b0 = mk(m, k0), mk(n, k0)
+    a1, b1 = (mk(m, k1), mk(n, k1)) if k1 else (None, None)
+    bias = torch.randn(n, generator=g).to(DEV)
+    div = torch.randint(1, 9, (m,), generator=g).float().to(DEV)
+    out = ops.gemm_nt(a0, b0, a1, b1, bias=bias, row_div=div, out_dtype=torch.float32)
+    ref = a0.double() @ b0.double().t()
+    if k1:
+        ref = ref + a1.double() @ b1.double().t()
+    ref = (ref + bias.double()) / div.double()[:, None]
+    scale = ref.abs().max().item()
+    err = (out.double() - ref).abs().max().item()
+    assert err <= tol * scale, f"max err {err} vs scale {scale}"
+    out2 = ops.gemm_nt(a0, b0, a1, b1, out_dtype=dtype)                 # output in the activation dtype, no epilogue
+    ref2 = a0.double() @ b0.double().t() + (a1.double() @ b1.double().t() if k1 else 0)
+    assert (out2.double() - ref2).abs().max().item() <= 2 * tol * ref2.abs().max().item()
+
+
+def test_sage_layer_fn_matches_torch():
+    """Fused layer Function (aggregate + dual GEMM, and their gradients) vs torch autograd on the same inputs."""
+    from pipegcn_b200 import ops
+    from pipegcn_b200.graph import PartGraph
+    from tests.helpers import small_world
+    _, _, layouts, _ = small_world("tiny", 2)
+    L = layouts[0]
+    graph = PartGraph.from_layout(L, device=DEV, seg_len=64)
+    d_in, d_out = 24, 16
+    torch.manual_seed(0)
+    feat = torch.randn(L.num_all, d_in, device=DEV, requires_grad=True)
+    w1 = torch.randn(d_out, d_in, device=DEV, requires_grad=True)
+    w2 = torch.randn(d_out, d_in, device=DEV, requires_grad=True)
+    b1 = torch.randn(d_out, device=DEV, requires_grad=True)
+    b2 = torch.randn(d_out, device=DEV, requires_grad=True)
+    go = torch.randn(L.num_in, d_out, device=DEV)
+    out = ops.sage_layer(feat, graph, graph.in_deg_f, w1, b1, w2, b2)
+    out.backward(go)
+    got = [out.detach().clone()] + [t.grad.clone() for t in (feat, w1, b1, w2, b2)]
+    for t in (feat, w1, b1, w2, b2):
+        t.grad = None
+    rows = torch.repeat_interleave(torch.arange(L.num_in, device=DEV), (L.indptr[1:] - L.indptr[:-1]).long().to(DEV))
+    A = torch.zeros(L.num_in, L.num_all, device=DEV)
+    A.index_put_((rows, L.indices.long().to(DEV)), torch.ones(rows.numel(), device=DEV), accumulate=True)
+    torch.backends.cuda.matmul.allow_tf32 = False
+    ah = (A @ feat) / graph.in_deg_f[:, None]
+    ref = feat[: L.num_in] @ w1.t() + b1 + ah @ w2.t() + b2
+    ref.backward(go)
+    want = [ref.detach()] + [t.grad for t in (feat, w1, b1, w2, b2)]
+    for a, b in zip(got, want):
+        assert (a - b).abs().max().item() <= 1e-4 * b.abs().max().item() + 1e-5     # 3xTF32 tensor-core product

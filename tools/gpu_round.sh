@@ -11,7 +11,7 @@ echo "== pytest gpu"; timeout 900 python -m pytest tests -m gpu -x -q > $OUT/pyt
 echo "== bench small"; timeout 300 python bench.py --workload small --steps 5 --warmup 3 --no-cpu-baseline > $OUT/bench_small.json 2> $OUT/bench_small.err; echo "rc=$?"; tail -2 $OUT/bench_small.err; cat $OUT/bench_small.json
 echo "== bench"; timeout 900 python bench.py --steps 20 --warmup 3 > $OUT/bench.json 2> $OUT/bench.err; echo "rc=$?"; tail -5 $OUT/bench.err; cat $OUT/bench.json
 if [ "${SKIP_NCU:-0}" != "1" ]; then
-echo "== ncu launches"; timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file $OUT/launches.csv python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-e2e > $OUT/ncu_launches.log 2>&1; echo "rc=$?"
-echo "== ncu full agg"; timeout 600 ncu --set full --clock-control none --import-source on -k regex:agg_kernel -s 6 -c 4 -o $OUT/prof_agg -f python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-e2e > $OUT/ncu_full.log 2>&1; echo "rc=$?"; tail -3 $OUT/ncu_full.log
+echo "== ncu launches"; timeout 600 ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none -c 1500 --csv --log-file $OUT/launches.csv python bench.py --steps 2 --warmup 2 --no-cpu-baseline --no-e2e --ncu-region > $OUT/ncu_launches.log 2>&1; echo "rc=$?"
+echo "== ncu full agg"; timeout 600 ncu --profile-from-start off --set full --clock-control none --import-source on -k regex:"agg_kernel|linear_tcgen05" -c 8 -o $OUT/prof_agg -f python bench.py --steps 1 --warmup 2 --no-cpu-baseline --no-e2e --ncu-region > $OUT/ncu_full.log 2>&1; echo "rc=$?"; tail -3 $OUT/ncu_full.log
 fi
 ls -la $OUT
