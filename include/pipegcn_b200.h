@@ -38,6 +38,8 @@ int pg_abi_version(void);
 const char* pg_last_error(void);
 /* writes sm major*10+minor, SM count and L2 bytes of `device`; needs a GPU */
 int pg_device_info(int device, int* sm_arch, int* sm_count, int64_t* l2_bytes);
+/* tuning knobs (process-wide): "agg_unroll" = 4 | 8 neighbour rows in flight per lane group */
+int pg_set_option(const char* name, int value);
 
 /* ------------------------------------------------------------------------------------------
  * Adjacency of one partition in CSR form plus the split of its long rows.
@@ -57,6 +59,7 @@ typedef struct pg_csr {
   const int32_t* long_row;      /* [n_long] row id */
   const int32_t* long_seg_ptr;  /* [n_long + 1] first segment of every long row */
   const int32_t* seg_long;      /* [n_seg] index into long_row */
+  const int32_t* row_order;     /* [n_rows] processing order of the rows (e.g. by falling degree), or NULL */
 } pg_csr;
 
 /*
@@ -127,8 +130,10 @@ typedef struct pg_msg {
 /* rows per CTA used by pg_halo_push when the host fills cta_begin */
 int pg_push_rows_per_cta(void);
 
+/* momentum = m and one_minus = (float)(1 - m) evaluated in double precision by the caller, exactly the two
+ * scalars of `t *= m; t += (1 - m) * recv` (feature_buffer.py:190-191) */
 int pg_halo_push(const pg_msg* msgs, int32_t n_msgs, int32_t n_ctas, const void* src, int64_t ld_src, int32_t d,
-                 int dtype, float momentum, uint32_t value, void* stream);
+                 int dtype, float momentum, float one_minus, uint32_t value, void* stream);
 
 /*
  * Block the stream until every flags[i] >= value (acquire, system scope).  A bounded spin:

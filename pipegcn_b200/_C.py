@@ -23,7 +23,7 @@ class PgError(RuntimeError):
 class pg_csr(C.Structure):
     _fields_ = [("indptr", C.c_void_p), ("indices", C.c_void_p), ("n_rows", C.c_int32), ("seg_len", C.c_int32),
                 ("n_long", C.c_int32), ("n_seg", C.c_int32), ("long_row", C.c_void_p), ("long_seg_ptr", C.c_void_p),
-                ("seg_long", C.c_void_p)]
+                ("seg_long", C.c_void_p), ("row_order", C.c_void_p)]
 
 
 class pg_gemm_src(C.Structure):
@@ -46,12 +46,13 @@ def _load():
         "pg_abi_version": (C.c_int, []),
         "pg_last_error": (C.c_char_p, []),
         "pg_device_info": (C.c_int, [C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(i64)]),
+        "pg_set_option": (C.c_int, [C.c_char_p, C.c_int]),
         "pg_aggregate": (C.c_int, [C.POINTER(pg_csr), vp, i64, vp, i64, i32, C.c_int, vp, i32, vp, vp]),
         "pg_row_div": (C.c_int, [vp, i64, vp, i64, i32, i32, C.c_int, vp, vp]),
         "pg_linear": (C.c_int, [C.c_int, C.c_int, C.POINTER(pg_gemm_src), i32, vp, vp, vp, i64, i32, i32, vp]),
         "pg_split_tf32": (C.c_int, [vp, i64, vp, vp, i64, i32, i32, vp]),
         "pg_push_rows_per_cta": (C.c_int, []),
-        "pg_halo_push": (C.c_int, [vp, i32, i32, vp, i64, i32, C.c_int, f32, u32, vp]),
+        "pg_halo_push": (C.c_int, [vp, i32, i32, vp, i64, i32, C.c_int, f32, f32, u32, vp]),
         "pg_halo_wait": (C.c_int, [vp, i32, u32, i32, vp, vp]),
         "pg_boundary_add": (C.c_int, [vp, i64, vp, i64, i32, C.c_int, vp, vp, vp, i32, vp]),
         "pg_heap_alloc": (C.c_int, [C.c_size_t, C.POINTER(vp)]),
@@ -70,6 +71,9 @@ def _load():
 
 
 lib, EXPORTS = _load()
+for _k, _v in (("agg_unroll", os.environ.get("PG_AGG_UNROLL")),):
+    if _v:
+        lib.pg_set_option(_k.encode(), int(_v))
 
 
 def check(rc: int, what: str = ""):

@@ -10,28 +10,28 @@
 // segments reduced by different groups into fp32 partials and summed in segment order by a
 // fix-up kernel: deterministic, no atomics.
 #include <algorithm>
+#include <string.h>
 #include "common.cuh"
 
 namespace pg {
 
 template <typename T, int VB, int G, int VPL, int U>
 __global__ void __launch_bounds__(256)
-agg_kernel(pg_csr g, const T* __restrict__ x, int64_t ldx, T* __restrict__ out, int64_t ldo, int nvec,
+agg_kernel(pg_csr g, const T* __restrict__ x, uint32_t ldx_bytes, T* __restrict__ out, int64_t ldo, int nvec,
            const float* __restrict__ row_div, int acc_rows, float* __restrict__ scratch, int64_t lds) {
   using P = Pack<T, VB>;
   using Raw = typename P::Raw;
   constexpr int V = P::V;
+  constexpr int NA = P::NA;
   constexpr int GROUPS = 256 / G;
-  const int lane = threadIdx.x & 31;
   const int lane_g = threadIdx.x % G;
-  const unsigned gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << (lane & ~(G - 1)));
   const int64_t item = static_cast<int64_t>(blockIdx.x) * GROUPS + threadIdx.x / G;
   const int64_t n_items = static_cast<int64_t>(g.n_rows) + g.n_seg;
   if (item >= n_items) return;   // whole group leaves together
 
   int row, beg, end, seg = -1;
   if (item < g.n_rows) {
-    row = static_cast<int>(item);
+    row = g.row_order ? __ldg(g.row_order + item) : static_cast<int>(item);
     beg = __ldg(g.indptr + row);
     end = __ldg(g.indptr + row + 1);
     if (end - beg > g.seg_len) return;   // long row: its segments do the work
@@ -46,48 +46,45 @@ agg_kernel(pg_csr g, const T* __restrict__ x, int64_t ldx, T* __restrict__ out, 
   }
 
   for (int c0 = 0; c0 < nvec; c0 += G * VPL) {
-    float acc[VPL][V];
+    float2 acc[VPL][NA];
 #pragma unroll
     for (int j = 0; j < VPL; ++j)
 #pragma unroll
-      for (int i = 0; i < V; ++i) acc[j][i] = 0.f;
+      for (int i = 0; i < NA; ++i) acc[j][i] = make_float2(0.f, 0.f);
     bool act[VPL];
-    int64_t off[VPL];
+    const char* xc[VPL];                   // this lane's column(s) of row 0
 #pragma unroll
     for (int j = 0; j < VPL; ++j) {
       const int vi = c0 + lane_g + j * G;
       act[j] = vi < nvec;
-      off[j] = static_cast<int64_t>(vi) * V;
+      xc[j] = reinterpret_cast<const char*>(x + static_cast<int64_t>(vi) * V);
     }
 
-    for (int e0 = beg; e0 < end; e0 += G) {
-      const int n = min(G, end - e0);
-      const int my = (lane_g < n) ? __ldg(g.indices + e0 + lane_g) : 0;
-      for (int k = 0; k < n; k += U) {
-        Raw v[U][VPL];
-        bool ok[U];
+    // main loop: U neighbour rows per batch, no tail predicates: U index loads (one broadcast
+    // transaction each), then U*VPL 16-byte row loads in flight before the first add.
+    // row address = base + src * ldx: one 32x32+64 multiply-add (IMAD.WIDE.U32) per row.
+    int e = beg;
+    for (; e + U <= end; e += U) {
+      uint32_t src[U];
 #pragma unroll
-        for (int u = 0; u < U; ++u) {
-          const int s = __shfl_sync(gmask, my, (k + u) % G, G);
-          ok[u] = (k + u) < n;
-          const T* rp = x + static_cast<int64_t>(s) * ldx;
+      for (int u = 0; u < U; ++u) src[u] = static_cast<uint32_t>(__ldg(g.indices + e + u));
+      Raw v[U][VPL];
 #pragma unroll
-          for (int j = 0; j < VPL; ++j)
-            if (ok[u] && act[j]) v[u][j] = ld_vec<VB>(rp + off[j]);
-        }
+      for (int u = 0; u < U; ++u)
 #pragma unroll
-        for (int u = 0; u < U; ++u) {
-          if (!ok[u]) continue;
+        for (int j = 0; j < VPL; ++j)
+          if (act[j]) v[u][j] = ld_vec<VB>(xc[j] + static_cast<uint64_t>(src[u]) * ldx_bytes);
 #pragma unroll
-          for (int j = 0; j < VPL; ++j) {
-            if (!act[j]) continue;
-            float f[V];
-            P::unpack(v[u][j], f);
+      for (int u = 0; u < U; ++u)
 #pragma unroll
-            for (int i = 0; i < V; ++i) acc[j][i] += f[i];
-          }
-        }
-      }
+        for (int j = 0; j < VPL; ++j)
+          if (act[j]) P::add(acc[j], v[u][j]);
+    }
+    for (; e < end; ++e) {
+      const uint32_t s = static_cast<uint32_t>(__ldg(g.indices + e));
+#pragma unroll
+      for (int j = 0; j < VPL; ++j)
+        if (act[j]) P::add(acc[j], ld_vec<VB>(xc[j] + static_cast<uint64_t>(s) * ldx_bytes));
     }
 
     if (seg >= 0) {
@@ -95,8 +92,9 @@ agg_kernel(pg_csr g, const T* __restrict__ x, int64_t ldx, T* __restrict__ out, 
 #pragma unroll
       for (int j = 0; j < VPL; ++j) {
         if (!act[j]) continue;
+        const int64_t o = static_cast<int64_t>(c0 + lane_g + j * G) * V;
 #pragma unroll
-        for (int i = 0; i < V; ++i) sp[off[j] + i] = acc[j][i];
+        for (int i = 0; i < V; ++i) sp[o + i] = (i & 1) ? acc[j][i / 2].y : acc[j][i / 2].x;
       }
     } else {
       const float dv = row_div ? __ldg(row_div + row) : 1.f;
@@ -104,16 +102,20 @@ agg_kernel(pg_csr g, const T* __restrict__ x, int64_t ldx, T* __restrict__ out, 
 #pragma unroll
       for (int j = 0; j < VPL; ++j) {
         if (!act[j]) continue;
+        const int64_t o = static_cast<int64_t>(c0 + lane_g + j * G) * V;
         float r[V];
 #pragma unroll
-        for (int i = 0; i < V; ++i) r[i] = row_div ? acc[j][i] / dv : acc[j][i];
-        if (row < acc_rows) {
-          float o[V];
-          P::unpack(*reinterpret_cast<const Raw*>(op + off[j]), o);
-#pragma unroll
-          for (int i = 0; i < V; ++i) r[i] += o[i];
+        for (int i = 0; i < V; ++i) {
+          const float a = (i & 1) ? acc[j][i / 2].y : acc[j][i / 2].x;
+          r[i] = row_div ? a / dv : a;
         }
-        st_vec<VB>(op + off[j], P::pack(r));
+        if (row < acc_rows) {
+          float ov[V];
+          P::unpack(*reinterpret_cast<const Raw*>(op + o), ov);
+#pragma unroll
+          for (int i = 0; i < V; ++i) r[i] += ov[i];
+        }
+        st_vec<VB>(op + o, P::pack(r));
       }
     }
   }
@@ -152,15 +154,29 @@ agg_fixup_kernel(pg_csr g, T* __restrict__ out, int64_t ldo, int nvec, const flo
   }
 }
 
+int g_agg_unroll = 8;   // pg_set_option("agg_unroll", 4|8): neighbour rows in flight per group (VPL == 1)
+
+template <typename T, int VB, int G, int VPL, int U>
+static int launch_agg_u(const pg_csr& g, const T* x, int64_t ldx, T* out, int64_t ldo, int nvec,
+                        const float* row_div, int acc_rows, float* scratch, int64_t lds, cudaStream_t st);
+
 template <typename T, int VB, int G, int VPL>
 static int launch_agg(const pg_csr& g, const T* x, int64_t ldx, T* out, int64_t ldo, int nvec,
                       const float* row_div, int acc_rows, float* scratch, int64_t lds, cudaStream_t st) {
-  constexpr int U = (VPL >= 4) ? 2 : 4;
+  if (VPL == 1 && g_agg_unroll == 4)
+    return launch_agg_u<T, VB, G, VPL, 4>(g, x, ldx, out, ldo, nvec, row_div, acc_rows, scratch, lds, st);
+  constexpr int U = (VPL >= 4) ? 2 : (VPL == 2 ? 4 : 8);
+  return launch_agg_u<T, VB, G, VPL, U>(g, x, ldx, out, ldo, nvec, row_div, acc_rows, scratch, lds, st);
+}
+
+template <typename T, int VB, int G, int VPL, int U>
+static int launch_agg_u(const pg_csr& g, const T* x, int64_t ldx, T* out, int64_t ldo, int nvec,
+                        const float* row_div, int acc_rows, float* scratch, int64_t lds, cudaStream_t st) {
   constexpr int GROUPS = 256 / G;
   const int64_t n_items = static_cast<int64_t>(g.n_rows) + g.n_seg;
   if (n_items > 0) {
     const int64_t blocks = (n_items + GROUPS - 1) / GROUPS;
-    agg_kernel<T, VB, G, VPL, U><<<static_cast<unsigned>(blocks), 256, 0, st>>>(g, x, ldx, out, ldo, nvec, row_div,
+    agg_kernel<T, VB, G, VPL, U><<<static_cast<unsigned>(blocks), 256, 0, st>>>(g, x, static_cast<uint32_t>(ldx * sizeof(T)), out, ldo, nvec, row_div,
                                                                                 acc_rows, scratch, lds);
     PG_LAUNCH_CHECK();
   }
@@ -263,11 +279,22 @@ static int row_div_t(const void* x, int64_t ldx, void* out, int64_t ldo, int n_r
 
 }  // namespace pg
 
+extern "C" int pg_set_option(const char* name, int value) {
+  PG_REQUIRE(name != nullptr, "pg_set_option: null name");
+  if (strcmp(name, "agg_unroll") == 0) {
+    PG_REQUIRE(value == 4 || value == 8, "agg_unroll must be 4 or 8");
+    pg::g_agg_unroll = value;
+    return PG_OK;
+  }
+  pg::set_error("pg_set_option: unknown option '%s'", name);
+  return PG_ERR_INVALID;
+}
+
 extern "C" int pg_aggregate(const pg_csr* g, const void* x, int64_t ldx, void* out, int64_t ldo, int32_t d, int dtype,
                             const float* row_div, int32_t acc_rows, float* scratch, void* stream) {
   PG_REQUIRE(g && x && out, "pg_aggregate: null argument");
   PG_REQUIRE(g->n_rows >= 0 && g->seg_len > 0 && d > 0, "pg_aggregate: bad sizes (n_rows=%d seg_len=%d d=%d)", g->n_rows, g->seg_len, d);
-  PG_REQUIRE(ldx >= d && ldo >= d, "pg_aggregate: row stride smaller than d");
+  PG_REQUIRE(ldx >= d && ldo >= d && ldx < (1ll << 29), "pg_aggregate: row stride smaller than d (or >= 2^29 elements)");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (dtype == PG_F32) return pg::aggregate_t<float>(*g, x, ldx, out, ldo, d, row_div, acc_rows, scratch, st);
   if (dtype == PG_BF16) return pg::aggregate_t<__nv_bfloat16>(*g, x, ldx, out, ldo, d, row_div, acc_rows, scratch, st);

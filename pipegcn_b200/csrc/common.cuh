@@ -54,11 +54,14 @@ __device__ __forceinline__ void st_vec(void* p, typename RawVec<VB>::type v) {
   *reinterpret_cast<typename RawVec<VB>::type*>(p) = v;
 }
 
-// ---- unpack VB bytes of T into floats / pack back ------------------------------------------
+// ---- unpack VB bytes of T into floats / pack back / accumulate -------------------------------
+// Accumulators are float2 pairs so that the adds are the packed fp32x2 instruction of sm_100
+// (FADD2: `__fadd2_rn`), half the issue slots of scalar FADD on this issue-bound gather.
 template <typename T, int VB> struct Pack;
 
 template <int VB> struct Pack<float, VB> {
   static constexpr int V = VB / 4;
+  static constexpr int NA = (V + 1) / 2;      // float2 accumulators per vector
   using Raw = typename RawVec<VB>::type;
   __device__ __forceinline__ static void unpack(const Raw& r, float* f) {
     const float* p = reinterpret_cast<const float*>(&r);
@@ -72,15 +75,32 @@ template <int VB> struct Pack<float, VB> {
     for (int i = 0; i < V; ++i) p[i] = f[i];
     return r;
   }
+  __device__ __forceinline__ static void add(float2* acc, const Raw& r) {
+    const float* p = reinterpret_cast<const float*>(&r);
+    if constexpr (V == 1) {
+      acc[0].x += p[0];
+    } else {
+#pragma unroll
+      for (int i = 0; i < NA; ++i) acc[i] = __fadd2_rn(acc[i], make_float2(p[2 * i], p[2 * i + 1]));
+    }
+  }
 };
 
 template <int VB> struct Pack<__nv_bfloat16, VB> {
   static constexpr int V = VB / 2;
+  static constexpr int NA = (V + 1) / 2;
   using Raw = typename RawVec<VB>::type;
   __device__ __forceinline__ static void unpack(const Raw& r, float* f) {
-    const uint16_t* p = reinterpret_cast<const uint16_t*>(&r);
+    if constexpr (V == 1) {
+      f[0] = __uint_as_float(static_cast<uint32_t>(*reinterpret_cast<const uint16_t*>(&r)) << 16);
+    } else {
+      const uint32_t* w = reinterpret_cast<const uint32_t*>(&r);
 #pragma unroll
-    for (int i = 0; i < V; ++i) f[i] = __uint_as_float(static_cast<uint32_t>(p[i]) << 16);
+      for (int i = 0; i < V / 2; ++i) {           // one word = two bf16: low half, high half
+        f[2 * i] = __uint_as_float(w[i] << 16);
+        f[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+      }
+    }
   }
   __device__ __forceinline__ static Raw pack(const float* f) {
     Raw r;
@@ -88,6 +108,16 @@ template <int VB> struct Pack<__nv_bfloat16, VB> {
 #pragma unroll
     for (int i = 0; i < V; ++i) p[i] = __float2bfloat16_rn(f[i]);
     return r;
+  }
+  __device__ __forceinline__ static void add(float2* acc, const Raw& r) {
+    if constexpr (V == 1) {
+      acc[0].x += __uint_as_float(static_cast<uint32_t>(*reinterpret_cast<const uint16_t*>(&r)) << 16);
+    } else {
+      const uint32_t* w = reinterpret_cast<const uint32_t*>(&r);
+#pragma unroll
+      for (int i = 0; i < NA; ++i)
+        acc[i] = __fadd2_rn(acc[i], make_float2(__uint_as_float(w[i] << 16), __uint_as_float(w[i] & 0xffff0000u)));
+    }
   }
 };
 

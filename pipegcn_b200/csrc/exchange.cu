@@ -144,11 +144,10 @@ static int common_vec(int d, int es, int vb, std::initializer_list<int64_t> lds)
 
 template <typename T>
 static int halo_push_t(const pg_msg* msgs, int n_msgs, int n_ctas, const void* src, int64_t ld_src, int d,
-                       int vb, float momentum, uint32_t value, cudaStream_t st) {
+                       int vb, float momentum, float one_minus, uint32_t value, cudaStream_t st) {
   const int es = sizeof(T);
   const int v = vb / es;
   const int nvec = static_cast<int>(round_up(d, v) / v);
-  const float one_minus = static_cast<float>(1.0 - static_cast<double>(momentum));
   const T* sp = static_cast<const T*>(src);
   if (n_ctas > 0) {
     switch (vb) {
@@ -170,7 +169,7 @@ extern "C" int pg_push_rows_per_cta(void) { return pg::kPushRows; }
 // Buffer.init_buffer with the same padded stride, the host passes d and strides, and the
 // widest vector legal for src is used; destinations must be at least as aligned.
 extern "C" int pg_halo_push(const pg_msg* msgs, int32_t n_msgs, int32_t n_ctas, const void* src, int64_t ld_src,
-                            int32_t d, int dtype, float momentum, uint32_t value, void* stream) {
+                            int32_t d, int dtype, float momentum, float one_minus, uint32_t value, void* stream) {
   PG_REQUIRE(msgs && n_msgs > 0, "pg_halo_push: no messages");
   PG_REQUIRE(src != nullptr || n_ctas == 0, "pg_halo_push: null source");
   PG_REQUIRE(d > 0 && ld_src >= d, "pg_halo_push: bad sizes");
@@ -180,8 +179,8 @@ extern "C" int pg_halo_push(const pg_msg* msgs, int32_t n_msgs, int32_t n_ctas, 
   int vb = pg::vec_bytes(src, ld_src, es);
   vb = pg::common_vec(d, es, vb, {ld_src});
   int rc;
-  if (dtype == PG_F32) rc = pg::halo_push_t<float>(msgs, n_msgs, n_ctas, src, ld_src, d, vb, momentum, value, st);
-  else if (dtype == PG_BF16) rc = pg::halo_push_t<__nv_bfloat16>(msgs, n_msgs, n_ctas, src, ld_src, d, vb, momentum, value, st);
+  if (dtype == PG_F32) rc = pg::halo_push_t<float>(msgs, n_msgs, n_ctas, src, ld_src, d, vb, momentum, one_minus, value, st);
+  else if (dtype == PG_BF16) rc = pg::halo_push_t<__nv_bfloat16>(msgs, n_msgs, n_ctas, src, ld_src, d, vb, momentum, one_minus, value, st);
   else { pg::set_error("pg_halo_push: unknown dtype %d", dtype); return PG_ERR_INVALID; }
   if (rc != PG_OK) return rc;
   pg::halo_flag_only_kernel<<<(n_msgs + 63) / 64, 64, 0, st>>>(msgs, n_msgs, value);

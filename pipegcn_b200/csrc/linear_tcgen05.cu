@@ -34,7 +34,9 @@ constexpr int kMaxSrc = 6;              // 2 operands pairs x 3 passes of the sp
 struct GemmMaps {
   CUtensorMap a[kMaxSrc];
   CUtensorMap b[kMaxSrc];
+  CUtensorMap c;             // output, box = [32 rows, 128 bytes], used by the TMA-store epilogue
 };
+constexpr int kSlabBytes = 32 * kRowBytes;     // one epilogue warp's staging slab: 32 rows x 128 B
 
 struct GemmArgs {
   int m, n, n_pad;
@@ -49,6 +51,7 @@ struct GemmArgs {
   int tmem_cols;             // power of two >= 2 * n_pad
   uint32_t idesc;
   int is_tf32;
+  int tma_store;             // 1: epilogue stages through shared memory and stores with TMA
 };
 
 // ---- PTX wrappers ------------------------------------------------------------------------------
@@ -80,6 +83,11 @@ __device__ __forceinline__ void tma_load_2d(uint32_t smem, const CUtensorMap* ma
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
       ::"r"(smem), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1)
       : "memory");
+}
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t smem, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(map)), "r"(smem), "r"(c0), "r"(c1)
+               : "memory");
 }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -144,7 +152,7 @@ __device__ __forceinline__ void store_chunk(const GemmArgs& p, int row, int c0, 
   for (int i = 0; i < CNT; ++i) {
     v[i] = __uint_as_float(r[i]);
     if (p.bias != nullptr && c0 + i < p.n) v[i] += __ldg(p.bias + c0 + i);
-    if (p.row_div != nullptr) v[i] = v[i] / dv;
+    if (p.row_div != nullptr) v[i] = v[i] * (1.f / dv);
   }
   const bool full = (c0 + CNT <= p.n);
   if (p.out_bf16) {
@@ -184,7 +192,9 @@ linear_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const GemmArgs p) {
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int b_bytes = p.n_pad * kRowBytes;
   const int stage_bytes = kABytes + b_bytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * stage_bytes);
+  uint8_t* slabs = smem + kStages * stage_bytes;                          // 4 x 4 KB, 1024-byte aligned
+  float* s_bias = reinterpret_cast<float*>(slabs + 4 * kSlabBytes);       // [256]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(slabs + 4 * kSlabBytes + 1024);
   uint64_t* full_bar = bars;                    // [kStages]
   uint64_t* empty_bar = bars + kStages;         // [kStages]
   uint64_t* tfull_bar = bars + 2 * kStages;     // [2]
@@ -201,6 +211,8 @@ linear_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const GemmArgs p) {
       asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&maps.b[s])) : "memory");
     }
   }
+  for (int i = threadIdx.x; i < 256; i += kGemmThreads)
+    s_bias[i] = (p.bias != nullptr && i < p.n) ? __ldg(p.bias + i) : 0.f;
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < kStages; ++s) {
       mbar_init(smem_u32(full_bar + s), 1);
@@ -278,30 +290,95 @@ linear_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const GemmArgs p) {
     const int q = warp - 4;                                  // == warp % 4: TMEM lane quarter
     int as = 0;
     uint32_t aphase = 0;
-    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-      mbar_wait(smem_u32(tfull_bar + as), aphase);
-      tc_fence_after();
-      const int row = tile * kBlockM + q * 32 + lane;
-      const bool row_ok = row < p.m;
-      const float dv = (p.row_div != nullptr && row_ok) ? __ldg(p.row_div + row) : 1.f;
-      const uint32_t tbase = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(as * p.n_pad);
-      int c0 = 0;
-      for (; c0 + 32 <= p.n_pad; c0 += 32) {
-        uint32_t r[32];
-        tmem_ld32(tbase + c0, r);
-        tmem_ld_wait();
-        if (row_ok && c0 < p.n) store_chunk<32>(p, row, c0, r, 0.f, dv);
+    if (p.tma_store) {
+      // TMEM -> registers -> (bias, row scale, convert) -> 128B-swizzled smem slab -> TMA store:
+      // every global write is a full, coalesced 128-byte row segment issued by the copy engine
+      uint8_t* slab = slabs + q * kSlabBytes;
+      const uint32_t slab_u32 = smem_u32(slab);
+      const int cpc = p.out_bf16 ? 64 : 32;                  // columns per 128-byte chunk
+      const int xr = lane & 7;                               // swizzle phase of this thread's row
+      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        mbar_wait(smem_u32(tfull_bar + as), aphase);
+        tc_fence_after();
+        const int row0 = tile * kBlockM + q * 32;
+        const int row = row0 + lane;
+        const float scale = (p.row_div != nullptr && row < p.m) ? 1.f / __ldg(p.row_div + row) : 1.f;
+        const uint32_t tbase = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(as * p.n_pad);
+        uint8_t* my = slab + lane * kRowBytes;
+        for (int c0 = 0; c0 < p.n; c0 += cpc) {
+          if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // slab free again
+          __syncwarp();
+          for (int cc = 0; cc < cpc && c0 + cc < p.n_pad; cc += 16) {
+            uint32_t r[16];
+            tmem_ld16(tbase + c0 + cc, r);
+            tmem_ld_wait();
+            float v[16];
+#pragma unroll
+            for (int i = 0; i < 16; i += 4) {
+              const float4 b4 = *reinterpret_cast<const float4*>(s_bias + c0 + cc + i);
+              v[i] = (__uint_as_float(r[i]) + b4.x) * scale;
+              v[i + 1] = (__uint_as_float(r[i + 1]) + b4.y) * scale;
+              v[i + 2] = (__uint_as_float(r[i + 2]) + b4.z) * scale;
+              v[i + 3] = (__uint_as_float(r[i + 3]) + b4.w) * scale;
+            }
+            if (p.out_bf16) {                                // 16 columns = 2 chunks of 16 bytes
+#pragma unroll
+              for (int h = 0; h < 2; ++h) {
+                uint4 pk;
+                __nv_bfloat162* hp = reinterpret_cast<__nv_bfloat162*>(&pk);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) hp[j] = __floats2bfloat162_rn(v[8 * h + 2 * j], v[8 * h + 2 * j + 1]);
+                const int chunk = (cc >> 3) + h;
+                *reinterpret_cast<uint4*>(my + ((chunk ^ xr) << 4)) = pk;
+              }
+            } else {                                         // 16 columns = 4 chunks of 16 bytes
+#pragma unroll
+              for (int h = 0; h < 4; ++h) {
+                const int chunk = (cc >> 2) + h;
+                *reinterpret_cast<float4*>(my + ((chunk ^ xr) << 4)) =
+                    make_float4(v[4 * h], v[4 * h + 1], v[4 * h + 2], v[4 * h + 3]);
+              }
+            }
+          }
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          __syncwarp();
+          if (lane == 0 && row0 < p.m) {
+            tma_store_2d(&maps.c, slab_u32, c0, row0);
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(tempty_bar + as));
+        if (++as == 2) { as = 0; aphase ^= 1; }
       }
-      if (c0 < p.n_pad) {
-        uint32_t r[16];
-        tmem_ld16(tbase + c0, r);
-        tmem_ld_wait();
-        if (row_ok && c0 < p.n) store_chunk<16>(p, row, c0, r, 0.f, dv);
+      if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    } else {
+      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        mbar_wait(smem_u32(tfull_bar + as), aphase);
+        tc_fence_after();
+        const int row = tile * kBlockM + q * 32 + lane;
+        const bool row_ok = row < p.m;
+        const float dv = (p.row_div != nullptr && row_ok) ? __ldg(p.row_div + row) : 1.f;
+        const uint32_t tbase = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(as * p.n_pad);
+        int c0 = 0;
+        for (; c0 + 32 <= p.n_pad; c0 += 32) {
+          uint32_t r[32];
+          tmem_ld32(tbase + c0, r);
+          tmem_ld_wait();
+          if (row_ok && c0 < p.n) store_chunk<32>(p, row, c0, r, 0.f, dv);
+        }
+        if (c0 < p.n_pad) {
+          uint32_t r[16];
+          tmem_ld16(tbase + c0, r);
+          tmem_ld_wait();
+          if (row_ok && c0 < p.n) store_chunk<16>(p, row, c0, r, 0.f, dv);
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(tempty_bar + as));
+        if (++as == 2) { as = 0; aphase ^= 1; }
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(smem_u32(tempty_bar + as));
-      if (++as == 2) { as = 0; aphase ^= 1; }
     }
   }
 
@@ -396,9 +473,28 @@ extern "C" int pg_linear(int dtype_in, int dtype_out, const pg_gemm_src* srcs, i
     PG_CHECK_CUDA(cudaGetDevice(&dev));
     PG_CHECK_CUDA(cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev));
   }
+  {
+    // TMA-store epilogue when the output rows are 16-byte aligned (always true for engine buffers)
+    const int eso = p.out_bf16 ? 2 : 4;
+    p.tma_store = ((reinterpret_cast<uintptr_t>(c) & 15) == 0 && (ldc * eso) % 16 == 0) ? 1 : 0;
+    if (p.tma_store) {
+      EncodeTiledFn enc = get_encode();
+      cuuint64_t gdim[2] = {static_cast<cuuint64_t>(n), static_cast<cuuint64_t>(m)};
+      cuuint64_t gstride[1] = {static_cast<cuuint64_t>(ldc) * eso};
+      cuuint32_t box[2] = {static_cast<cuuint32_t>(kRowBytes / eso), 32};
+      cuuint32_t estr[2] = {1, 1};
+      CUresult r = enc(&maps.c, p.out_bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, c,
+                       gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                       CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(output) failed (%d)", (int)r); return PG_ERR_CUDA; }
+    } else {
+      maps.c = maps.a[0];
+    }
+  }
   const int n_tiles = (m + kBlockM - 1) / kBlockM;
   const int grid = n_tiles < g_sm_count ? n_tiles : g_sm_count;
-  const size_t smem = static_cast<size_t>(kStages) * (kABytes + p.n_pad * kRowBytes) + 1024 /*align*/ + 256 /*barriers*/;
+  const size_t smem = static_cast<size_t>(kStages) * (kABytes + p.n_pad * kRowBytes) + 4 * kSlabBytes /*staging*/ +
+                      1024 /*bias*/ + 256 /*barriers*/ + 1024 /*align*/;
   if (tf32) {
     PG_CHECK_CUDA(cudaFuncSetAttribute(linear_tcgen05_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
     linear_tcgen05_kernel<true><<<grid, kGemmThreads, smem, st>>>(maps, p);

@@ -18,7 +18,8 @@ from . import _C
 class CsrPlan:
     """Device CSR + the split of its long rows, packaged as a `pg_csr` for the C ABI."""
 
-    def __init__(self, indptr: torch.Tensor, indices: torch.Tensor, seg_len: Optional[int] = None):
+    def __init__(self, indptr: torch.Tensor, indices: torch.Tensor, seg_len: Optional[int] = None,
+                 sort_rows: bool = True):
         assert indptr.dtype == torch.int32 and indices.dtype == torch.int32
         self.indptr, self.indices = indptr.contiguous(), indices.contiguous()
         self.n_rows = int(indptr.numel() - 1)
@@ -44,9 +45,14 @@ class CsrPlan:
         self.n_long = n_long
         self.max_deg = int(deg.max().item()) if self.n_rows else 0
         self._scratch = None
+        # rows are handed to the warps by falling degree: the warps of a CTA get similar amounts of work
+        # (no CTA waits for one heavy row) and the heaviest rows start first
+        self.row_order = torch.argsort(deg, descending=True, stable=True).to(torch.int32).contiguous() \
+            if (self.n_rows and sort_rows) else None
         self.c = _C.pg_csr(self.indptr.data_ptr(), self.indices.data_ptr(), self.n_rows, self.seg_len, n_long,
                            self.n_seg, self.long_row.data_ptr(), self.long_seg_ptr.data_ptr(),
-                           self.seg_long.data_ptr())
+                           self.seg_long.data_ptr(),
+                           self.row_order.data_ptr() if self.row_order is not None else None)
 
     def scratch(self, d: int) -> Optional[torch.Tensor]:
         if self.n_seg == 0:

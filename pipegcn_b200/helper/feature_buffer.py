@@ -262,7 +262,8 @@ class Buffer(object):
             return
         _C.count(2)
         _C.check(_C.lib.pg_halo_push(ms.ptr, ms.n_msgs, ms.n_ctas, src.data_ptr(), src.stride(0), d,
-                                     _C.dtype_code(src.dtype), self._corr_momentum, value & 0xffffffff,
+                                     _C.dtype_code(src.dtype), self._corr_momentum, 1 - self._corr_momentum,
+                                     value & 0xffffffff,
                                      _C.stream_ptr()), "pg_halo_push")
 
     def _wait_flags(self, layer: int, direction: int, value: int, name: str):
