@@ -5,8 +5,6 @@ from pathlib import Path
 # several simulated ranks share one GPU in the LocalWorld tests, each with its own streams:
 # keep them on distinct hardware queues so that a flag-wait kernel cannot block its producer
 os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
-# a spinning flag-wait kernel must never have to wait for the lazy load of the kernel that feeds it
-os.environ.setdefault("CUDA_MODULE_LOADING", "EAGER")
 
 ROOT = Path(__file__).resolve().parent.parent
 if str(ROOT) not in sys.path:

@@ -1,0 +1,81 @@
+"""Multi-GPU parity: one process per GPU (torchrun), DistWorld + CUDA IPC + NVLink pushes, against the CPU oracle.
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 \
+        tools/dist_parity.py
+Every rank builds the same seeded tiny graph, runs the oracle world on the host (threads) and its own rank of the
+CUDA engine, and compares logits / losses / reduced gradients per epoch in the four exchange modes.
+"""
+import os
+import sys
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT))
+
+import torch
+import torch.distributed as dist
+
+MODES = {
+    "sync": dict(),
+    "sync_corr": dict(feat_corr=True, grad_corr=True, corr_momentum=0.9),
+    "pipeline": dict(enable_pipeline=True),
+    "pipeline_corr": dict(enable_pipeline=True, feat_corr=True, grad_corr=True, corr_momentum=0.95),
+}
+
+
+def main():
+    rank, size, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dev = torch.device(f"cuda:{local}")
+    dist.init_process_group("nccl", rank=rank, world_size=size, device_id=dev)
+    from oracle.train import initial_state, run_world
+    from pipegcn_b200.helper.feature_buffer import Buffer
+    from pipegcn_b200.helper.reducer import Reducer
+    from pipegcn_b200.train import RankEngine
+    from pipegcn_b200.world import DistWorld
+    from tests.helpers import make_args, small_world
+
+    shape = sys.argv[1] if len(sys.argv) > 1 else "tiny"
+    n_class = 5 if shape == "tiny" else 16
+    g, _, layouts, setups = small_world(shape, size)
+    n_epochs = 4
+    ok = True
+    for mode, kw in MODES.items():
+        oargs, eargs = make_args(g, n_class, n_epochs=n_epochs, **kw)
+        init = initial_state(oargs)
+        traces = run_world(setups, oargs, init_state=init)
+        world = DistWorld(device=dev)
+        eng = RankEngine(layouts[rank], eargs, world, init_state=init, seg_len=32)
+        worst = 0.0
+        for e in range(n_epochs):
+            loss = eng.forward_backward(keep_logits=True)
+            eng.finish_epoch()
+            eng.buffer.check_status()
+            eng.buffer.timer.clear()
+            ref = traces[rank]
+            d = (eng.last_logits.float().cpu() - ref.logits[e]).abs().max().item()
+            worst = max(worst, d / max(ref.logits[e].abs().max().item(), 1e-6))
+            dl = abs(float(loss.item()) - ref.losses[e]) / abs(ref.losses[e])
+            for n, p in eng.model.named_parameters():
+                gd = (p.grad.float().cpu() - ref.grads[e][n]).abs().max().item()
+                worst = max(worst, gd / max(ref.grads[e][n].abs().max().item(), 1e-6))
+            worst = max(worst, dl)
+        eng.buffer.synchronize()
+        torch.cuda.synchronize()
+        flag = torch.tensor([worst], device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MAX)
+        if rank == 0:
+            good = flag.item() < 2e-3
+            ok = ok and good
+            print(f"[dist_parity] {shape} P={size} mode={mode:14s} worst relative error {flag.item():.3e} "
+                  f"{'OK' if good else 'FAIL'}", flush=True)
+        del eng
+        dist.barrier()
+    dist.destroy_process_group()
+    if rank == 0:
+        print("[dist_parity] " + ("ALL OK" if ok else "FAILED"), flush=True)
+        sys.exit(0 if ok else 1)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,9 @@
+#!/bin/bash
+# multi-GPU round: IPC/NVLink parity against the oracle, then bench at this GPU count
+N=${1:-2}; TAG=${2:-m$N}
+OUT=gpurun_out/$TAG; mkdir -p $OUT
+export CUDA_DEVICE_MAX_CONNECTIONS=32
+nvidia-smi topo -m > $OUT/topo.txt 2>&1
+echo "== dist parity tiny"; timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 tools/dist_parity.py tiny > $OUT/parity_tiny.log 2>&1; echo "rc=$?"; grep dist_parity $OUT/parity_tiny.log | tail -6; tail -5 $OUT/parity_tiny.log | grep -v dist_parity
+echo "== dist parity small"; timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29512 tools/dist_parity.py small > $OUT/parity_small.log 2>&1; echo "rc=$?"; grep dist_parity $OUT/parity_small.log | tail -6
+echo "== bench x$N"; timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29513 bench.py --gpus $N --steps 20 --warmup 3 > $OUT/bench.json 2> $OUT/bench.err; echo "rc=$?"; tail -3 $OUT/bench.err; tail -1 $OUT/bench.json
