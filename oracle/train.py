@@ -71,6 +71,7 @@ class RankTrace:
     comm_time: List[float] = field(default_factory=list)
     reduce_time: List[float] = field(default_factory=list)
     wall: List[float] = field(default_factory=list)                 # every epoch, no exclusions
+    states: List[Dict[str, torch.Tensor]] = field(default_factory=list)   # weights at the START of every epoch
     hook_grads: Dict = field(default_factory=dict)                  # (epoch, layer) -> (grad in, grad out) of the halo hook
 
 
@@ -101,6 +102,8 @@ def run_rank(rs: RankSetup, args: OracleArgs, fabric, init_state=None, keep_trac
     for epoch in range(args.n_epochs):
         t0 = time.time()
         model.train()
+        if keep_trace:
+            tr.states.append({k: v.detach().clone() for k, v in model.state_dict().items()})
         ltrace = {} if keep_trace else None
         logits = model(graph, feat, in_deg, buf, trace=ltrace)
         loss = loss_fcn(logits[train_mask], labels)                       # train.py:351

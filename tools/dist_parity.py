@@ -48,6 +48,7 @@ def main():
         eng = RankEngine(layouts[rank], eargs, world, init_state=init, seg_len=32)
         worst = 0.0
         for e in range(n_epochs):
+            eng.model.load_state_dict(traces[0].states[e])      # teacher forcing, see tests/test_engine_gpu.py
             loss = eng.forward_backward(keep_logits=True)
             eng.finish_epoch()
             eng.buffer.check_status()
