@@ -75,7 +75,8 @@ class RankTrace:
     hook_grads: Dict = field(default_factory=dict)                  # (epoch, layer) -> (grad in, grad out) of the halo hook
 
 
-def run_rank(rs: RankSetup, args: OracleArgs, fabric, init_state=None, keep_trace=True, feat=None) -> RankTrace:
+def run_rank(rs: RankSetup, args: OracleArgs, fabric, init_state=None, keep_trace=True, feat=None,
+             forced_states=None) -> RankTrace:
     rank, size = rs.rank, rs.size
     timer = OracleCommTimer()
     buf = OracleBuffer(fabric, rank, size, timer)
@@ -102,6 +103,8 @@ def run_rank(rs: RankSetup, args: OracleArgs, fabric, init_state=None, keep_trac
     for epoch in range(args.n_epochs):
         t0 = time.time()
         model.train()
+        if forced_states is not None:           # teacher forcing: start every epoch from given weights
+            model.load_state_dict(forced_states[epoch])
         if keep_trace:
             tr.states.append({k: v.detach().clone() for k, v in model.state_dict().items()})
         ltrace = {} if keep_trace else None
@@ -133,14 +136,15 @@ def run_rank(rs: RankSetup, args: OracleArgs, fabric, init_state=None, keep_trac
     return tr
 
 
-def run_world(setups: List[RankSetup], args: OracleArgs, init_state=None, keep_trace=True) -> List[RankTrace]:
+def run_world(setups: List[RankSetup], args: OracleArgs, init_state=None, keep_trace=True,
+              forced_states=None) -> List[RankTrace]:
     """All ranks of a world as threads in this process."""
     size = len(setups)
     fabric = ThreadFabric(size)
     out: List[Optional[RankTrace]] = [None] * size
     err: List[Optional[BaseException]] = [None] * size
     if size == 1:
-        return [run_rank(setups[0], args, fabric, init_state, keep_trace)]
+        return [run_rank(setups[0], args, fabric, init_state, keep_trace, forced_states=forced_states)]
     torch.set_num_threads(max(1, torch.get_num_threads() // size))
 
     # every rank seeds the global RNG identically before building its model (train.py:298); with threads the
@@ -154,7 +158,7 @@ def run_world(setups: List[RankSetup], args: OracleArgs, init_state=None, keep_t
 
     def work(r):
         try:
-            out[r] = run_rank(setups[r], args, fabric, init_state, keep_trace)
+            out[r] = run_rank(setups[r], args, fabric, init_state, keep_trace, forced_states=forced_states)
         except BaseException as e:   # noqa: BLE001
             err[r] = e
             try:

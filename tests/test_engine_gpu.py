@@ -99,3 +99,42 @@ def test_exposed_comm_timer_sections():
     assert all(v >= 0 for v in sec.values())
     with pytest.raises(Exception):
         trainer.engines[0].buffer.timer.add_events("forward_0", None, None)   # duplicate name, as the reference
+
+
+@pytest.mark.parametrize("name", ["ref_sync_p2.pt", "ref_sync_corr_p2.pt", "ref_pipeline_p2.pt", "ref_pipeline_corr_p3.pt"])
+def test_engine_matches_reference_golden(name):
+    """The CUDA engine against the committed outputs of the unmodified reference (tests/golden): per-layer inputs
+    and outputs, logits, loss, reduced gradients; fp32, teacher-forced weights.  Tolerances: exchange/aggregate
+    outputs rtol 1e-5 (sum order), layer outputs/logits 2e-4 (3xTF32 tensor-core product), gradients 2e-3."""
+    from tests.test_golden_cpu import load
+    from pipegcn_b200.partition import build_layouts
+    from pipegcn_b200.train import LocalTrainer
+    from pipegcn_b200.world import LocalWorld
+    from tests.helpers import make_args
+    fx, g, part = load(name)
+    c = fx["config"]
+    P = c["n_parts"]
+    layouts = build_layouts(g, part, P)
+    _, eargs = make_args(g, c["n_class"], n_epochs=c["n_epochs"], n_layers=c["n_layers"], n_hidden=c["n_hidden"],
+                         enable_pipeline=c.get("enable_pipeline", False), feat_corr=c.get("feat_corr", False),
+                         grad_corr=c.get("grad_corr", False), corr_momentum=c.get("corr_momentum", 0.95))
+    trainer = LocalTrainer(layouts, eargs, LocalWorld(P, "cuda"), init_state=fx["ranks"][0]["init_state"], seg_len=32)
+    caps = [dict() for _ in range(P)]
+    for r, eng in enumerate(trainer.engines):
+        for i, layer in enumerate(eng.model.layers):
+            def hook(mod, inp, out, r=r, i=i):
+                caps[r][i] = (inp[1].detach(), out.detach())
+            layer.register_forward_hook(hook)
+    for e in range(c["n_epochs"]):
+        for eng in trainer.engines:
+            eng.model.load_state_dict(fx["ranks"][0]["epochs"][e]["state"])
+        losses = trainer.run_epoch(keep_logits=True)
+        for r, eng in enumerate(trainer.engines):
+            ep = fx["ranks"][r]["epochs"][e]
+            for i, rec in ep["layers"].items():
+                torch.testing.assert_close(caps[r][i][0].cpu(), rec["f_buf"], rtol=2e-4, atol=2e-5)
+                torch.testing.assert_close(caps[r][i][1].cpu(), rec["layer_out"], rtol=2e-4, atol=2e-4)
+            torch.testing.assert_close(eng.last_logits.cpu(), ep["logits"], rtol=2e-4, atol=2e-4)
+            assert abs(float(losses[r].item()) - ep["loss"]) <= 1e-4 * abs(ep["loss"])
+            for n, p in eng.model.named_parameters():
+                torch.testing.assert_close(p.grad.cpu(), ep["grads"][n], rtol=2e-3, atol=2e-5)
