@@ -229,7 +229,7 @@ def main():
 
     def step_e2e():
         engine.buffer.timer.clear()
-        engine.feat.copy_(feat_host, non_blocking=True)
+        engine.set_features(feat_host)
         engine.labels.copy_(label_host, non_blocking=True)
         loss = engine.run_epoch()
         return float(loss.item())      # device -> host read of the step's result

@@ -106,6 +106,29 @@ int pg_split_tf32(const float* x, int64_t ldx, float* hi, float* lo, int64_t ld,
                   void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Row-wise epilogues of the layer loop (model.py:53-56, train.py:320,351).  One warp per row, every tensor
+ * read once and written once; column reductions are two-stage (`partial`: fp32 scratch of
+ * pg_row_grid(n_rows) * 3 * d floats for the LayerNorm backward, pg_row_grid(n) * max(c, 1) for the loss).
+ * ---------------------------------------------------------------------------------------- */
+int pg_row_grid(int32_t n_rows);
+/* out = relu?(LayerNorm(y) * gamma + beta), mean/rstd [n_rows] kept for the backward; d % (16/elem) == 0 */
+int pg_ln_relu_fwd(const void* y, int64_t ldy, const float* gamma, const float* beta, float eps, int relu,
+                   void* out, int64_t ldo, float* mean, float* rstd, int32_t n_rows, int32_t d, int dtype,
+                   void* stream);
+/* g_y, dgamma[d], dbeta[d] and colsum[d] = column sums of g_y (the bias gradient of the producing linear) */
+int pg_ln_relu_bwd(const void* g_out, int64_t ldg, const void* out, int64_t ldo, const void* y, int64_t ldy,
+                   const float* mean, const float* rstd, const float* gamma, int relu, void* g_y, int64_t ldgy,
+                   float* dgamma, float* dbeta, float* colsum, float* partial, int32_t n_rows, int32_t d,
+                   int dtype, void* stream);
+/* loss[0] = sum_rows (logsumexp(z) - z[label]) over the first n_rows rows: CrossEntropyLoss(reduction='sum') */
+int pg_ce_fwd(const void* z, int64_t ld, const int64_t* labels, int32_t n_rows, int32_t c, int dtype, float* lse,
+              float* partial, float* loss, void* stream);
+/* g[r] = (softmax(z[r]) - onehot) * upstream[0] for r < n_rows, 0 for n_rows <= r < n_total; colsum[c] optional */
+int pg_ce_bwd(const void* z, int64_t ld, const int64_t* labels, const float* lse, const float* upstream,
+              int32_t n_rows, int32_t n_total, int32_t c, int dtype, void* g, int64_t ldg, float* colsum,
+              float* partial, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * Halo exchange (feature_buffer.py:165-194).  One descriptor per message of a launch; the
  * array lives in device memory and is built once by Buffer.init_buffer.
  * A message copies n_rows rows of `src` (gathered through idx, or contiguous from src_row0)

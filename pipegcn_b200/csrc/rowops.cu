@@ -1,0 +1,320 @@
+// Row-wise epilogue kernels of the layer loop, sm_100a, HBM-bound:
+//   * LayerNorm + ReLU forward in one pass              (/root/reference/module/model.py:53-56)
+//   * its backward, fused with the three column reductions the step needs (d gamma, d beta and the
+//     bias gradient of the linear that produced the pre-norm tensor)
+//   * summed soft-max cross-entropy forward / backward  (/root/reference/train.py:320,351)
+// One warp owns one row; a row of up to 32 lanes x kMaxVec 16-byte vectors stays in registers between
+// the statistics pass and the output pass, so every tensor is read once and written once.
+// Column reductions are two-stage and deterministic: per-CTA partials, then a fixed-order sum.
+#include "common.cuh"
+
+namespace pg {
+
+constexpr int kRowThreads = 256;
+constexpr int kMaxVec = 4;          // vectors per lane kept in registers (bf16: d <= 1024, fp32: d <= 512)
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(kRowThreads)
+ln_relu_fwd_kernel(const T* __restrict__ y, int64_t ldy, const float* __restrict__ gamma, const float* __restrict__ beta,
+                   float eps, int relu, T* __restrict__ out, int64_t ldo, float* __restrict__ mean_out,
+                   float* __restrict__ rstd_out, int n_rows, int d) {
+  using P = Pack<T, 16>;
+  constexpr int V = P::V;
+  const int lane = threadIdx.x & 31;
+  const int warps = (gridDim.x * kRowThreads) >> 5;
+  const int nvec = d / V;                                   // host guarantees d % V == 0 and nvec <= 32 * kMaxVec
+  for (int row = (blockIdx.x * kRowThreads + threadIdx.x) >> 5; row < n_rows; row += warps) {
+    const T* yp = y + static_cast<int64_t>(row) * ldy;
+    float x[kMaxVec][V];
+    float s = 0.f;
+#pragma unroll
+    for (int j = 0; j < kMaxVec; ++j) {
+      const int vi = lane + j * 32;
+      if (vi < nvec) {
+        P::unpack(*reinterpret_cast<const typename P::Raw*>(yp + static_cast<int64_t>(vi) * V), x[j]);
+#pragma unroll
+        for (int i = 0; i < V; ++i) s += x[j][i];
+      }
+    }
+    const float mean = warp_sum(s) / d;
+    float q = 0.f;
+#pragma unroll
+    for (int j = 0; j < kMaxVec; ++j)
+      if (lane + j * 32 < nvec)
+#pragma unroll
+        for (int i = 0; i < V; ++i) { const float c = x[j][i] - mean; q += c * c; }
+    const float rstd = rsqrtf(warp_sum(q) / d + eps);
+    if (lane == 0) { mean_out[row] = mean; rstd_out[row] = rstd; }
+    T* op = out + static_cast<int64_t>(row) * ldo;
+#pragma unroll
+    for (int j = 0; j < kMaxVec; ++j) {
+      const int vi = lane + j * 32;
+      if (vi < nvec) {
+        float r[V];
+#pragma unroll
+        for (int i = 0; i < V; ++i) {
+          const int c = vi * V + i;
+          float v = (x[j][i] - mean) * rstd * __ldg(gamma + c) + __ldg(beta + c);
+          r[i] = (relu && v < 0.f) ? 0.f : v;
+        }
+        st_vec<16>(op + static_cast<int64_t>(vi) * V, P::pack(r));
+      }
+    }
+  }
+}
+
+// g_y = rstd * (gh*gamma - mean_d(gh*gamma) - xhat * mean_d(gh*gamma*xhat)),  gh = g_out * (out > 0)
+// partial[blockIdx][0] += gh * xhat (d gamma), [1] += gh (d beta), [2] += g_y (bias gradient upstream)
+template <typename T>
+__global__ void __launch_bounds__(kRowThreads)
+ln_relu_bwd_kernel(const T* __restrict__ g_out, int64_t ldg, const T* __restrict__ out, int64_t ldo,
+                   const T* __restrict__ y, int64_t ldy, const float* __restrict__ mean, const float* __restrict__ rstd,
+                   const float* __restrict__ gamma, int relu, T* __restrict__ g_y, int64_t ldgy,
+                   float* __restrict__ partial, int n_rows, int d) {
+  using P = Pack<T, 16>;
+  using Raw = typename P::Raw;
+  constexpr int V = P::V;
+  extern __shared__ float red[];                             // [3][d]
+  const int lane = threadIdx.x & 31;
+  const int warps = (gridDim.x * kRowThreads) >> 5;
+  const int nvec = d / V;
+  float cg[kMaxVec][V], cb[kMaxVec][V], cy[kMaxVec][V];      // this lane's column partials
+#pragma unroll
+  for (int j = 0; j < kMaxVec; ++j)
+#pragma unroll
+    for (int i = 0; i < V; ++i) cg[j][i] = cb[j][i] = cy[j][i] = 0.f;
+
+  for (int row = (blockIdx.x * kRowThreads + threadIdx.x) >> 5; row < n_rows; row += warps) {
+    const float mu = __ldg(mean + row), rs = __ldg(rstd + row);
+    float gh[kMaxVec][V], xh[kMaxVec][V];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int j = 0; j < kMaxVec; ++j) {
+      const int vi = lane + j * 32;
+      if (vi < nvec) {
+        float g[V], o[V], yy[V];
+        P::unpack(*reinterpret_cast<const Raw*>(g_out + static_cast<int64_t>(row) * ldg + static_cast<int64_t>(vi) * V), g);
+        P::unpack(*reinterpret_cast<const Raw*>(y + static_cast<int64_t>(row) * ldy + static_cast<int64_t>(vi) * V), yy);
+        if (relu) P::unpack(*reinterpret_cast<const Raw*>(out + static_cast<int64_t>(row) * ldo + static_cast<int64_t>(vi) * V), o);
+#pragma unroll
+        for (int i = 0; i < V; ++i) {
+          const float gg = (relu && !(o[i] > 0.f)) ? 0.f : g[i];
+          const float xx = (yy[i] - mu) * rs;
+          gh[j][i] = gg;
+          xh[j][i] = xx;
+          const float gx = gg * __ldg(gamma + vi * V + i);
+          s1 += gx;
+          s2 += gx * xx;
+          cg[j][i] += gg * xx;
+          cb[j][i] += gg;
+        }
+      }
+    }
+    const float c1 = warp_sum(s1) / d, c2 = warp_sum(s2) / d;
+#pragma unroll
+    for (int j = 0; j < kMaxVec; ++j) {
+      const int vi = lane + j * 32;
+      if (vi < nvec) {
+        float r[V];
+#pragma unroll
+        for (int i = 0; i < V; ++i) {
+          r[i] = rs * (gh[j][i] * __ldg(gamma + vi * V + i) - c1 - xh[j][i] * c2);
+          // the tensor handed upstream is stored in T: reduce what is stored
+          cy[j][i] += (sizeof(T) == 2) ? __bfloat162float(__float2bfloat16_rn(r[i])) : r[i];
+        }
+        st_vec<16>(g_y + static_cast<int64_t>(row) * ldgy + static_cast<int64_t>(vi) * V, P::pack(r));
+      }
+    }
+  }
+  // CTA-level reduction of the column partials in a fixed order (warp 0..7), then one partial row per CTA
+  for (int i = threadIdx.x; i < 3 * d; i += kRowThreads) red[i] = 0.f;
+  __syncthreads();
+  for (int w = 0; w < kRowThreads / 32; ++w) {
+    if ((threadIdx.x >> 5) == w) {
+#pragma unroll
+      for (int j = 0; j < kMaxVec; ++j) {
+        const int vi = lane + j * 32;
+        if (vi < nvec)
+#pragma unroll
+          for (int i = 0; i < V; ++i) {
+            const int c = vi * V + i;
+            red[c] += cg[j][i];
+            red[d + c] += cb[j][i];
+            red[2 * d + c] += cy[j][i];
+          }
+      }
+    }
+    __syncthreads();
+  }
+  float* pp = partial + static_cast<int64_t>(blockIdx.x) * 3 * d;
+  for (int i = threadIdx.x; i < 3 * d; i += kRowThreads) pp[i] = red[i];
+}
+
+// out[k] = sum over blocks of partial[b][k], in block order
+__global__ void colsum_final_kernel(const float* __restrict__ partial, int n_blocks, int width, float* __restrict__ out0,
+                                    float* __restrict__ out1, float* __restrict__ out2, int d) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= width) return;
+  float s = 0.f;
+  for (int b = 0; b < n_blocks; ++b) s += partial[static_cast<int64_t>(b) * width + k];
+  float* o = (k < d) ? out0 : (k < 2 * d ? out1 : out2);
+  if (o != nullptr) o[k % d] = s;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// loss = sum_rows (logsumexp(z) - z[label]);  lse[row] kept for the backward
+template <typename T>
+__global__ void __launch_bounds__(kRowThreads)
+ce_fwd_kernel(const T* __restrict__ z, int64_t ld, const int64_t* __restrict__ labels, int n_rows, int c,
+              float* __restrict__ lse, float* __restrict__ partial) {
+  __shared__ float wsum[kRowThreads / 32];
+  const int lane = threadIdx.x & 31;
+  const int warps = (gridDim.x * kRowThreads) >> 5;
+  float acc = 0.f;
+  for (int row = (blockIdx.x * kRowThreads + threadIdx.x) >> 5; row < n_rows; row += warps) {
+    const T* zp = z + static_cast<int64_t>(row) * ld;
+    float m = -INFINITY;
+    for (int k = lane; k < c; k += 32) m = fmaxf(m, static_cast<float>(zp[k]));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    float s = 0.f;
+    for (int k = lane; k < c; k += 32) s += expf(static_cast<float>(zp[k]) - m);
+    s = warp_sum(s);
+    const float l = m + logf(s);
+    if (lane == 0) {
+      lse[row] = l;
+      acc += l - static_cast<float>(zp[labels[row]]);
+    }
+  }
+  if (lane == 0) wsum[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float s = 0.f;
+    for (int w = 0; w < kRowThreads / 32; ++w) s += wsum[w];
+    partial[blockIdx.x] = s;
+  }
+}
+
+// g[row, k] = (exp(z - lse) - [k == label]) * upstream   for row < n_rows, zero for n_rows <= row < n_total
+template <typename T>
+__global__ void __launch_bounds__(kRowThreads)
+ce_bwd_kernel(const T* __restrict__ z, int64_t ld, const int64_t* __restrict__ labels, const float* __restrict__ lse,
+              const float* __restrict__ upstream, int n_rows, int n_total, int c, T* __restrict__ g, int64_t ldg,
+              float* __restrict__ partial) {
+  extern __shared__ float red[];                             // [c]
+  const int lane = threadIdx.x & 31;
+  const int warps = (gridDim.x * kRowThreads) >> 5;
+  const float up = upstream ? __ldg(upstream) : 1.f;
+  for (int i = threadIdx.x; i < c; i += kRowThreads) red[i] = 0.f;
+  __syncthreads();
+  for (int row = (blockIdx.x * kRowThreads + threadIdx.x) >> 5; row < n_total; row += warps) {
+    T* gp = g + static_cast<int64_t>(row) * ldg;
+    if (row >= n_rows) {
+      for (int k = lane; k < c; k += 32) gp[k] = static_cast<T>(0.f);
+      continue;
+    }
+    const T* zp = z + static_cast<int64_t>(row) * ld;
+    const float l = lse[row];
+    const int lab = static_cast<int>(labels[row]);
+    for (int k = lane; k < c; k += 32) {
+      const float v = (expf(static_cast<float>(zp[k]) - l) - (k == lab ? 1.f : 0.f)) * up;
+      const T t = static_cast<T>(v);
+      gp[k] = t;
+      atomicAdd(&red[k], static_cast<float>(t));             // shared-memory partial; order fixed within a warp only
+    }
+  }
+  __syncthreads();
+  float* pp = partial + static_cast<int64_t>(blockIdx.x) * c;
+  for (int i = threadIdx.x; i < c; i += kRowThreads) pp[i] = red[i];
+}
+
+static int row_grid(int n_rows) {
+  const int need = (n_rows + (kRowThreads / 32) - 1) / (kRowThreads / 32);
+  return need < 148 * 4 ? (need > 0 ? need : 1) : 148 * 4;
+}
+
+}  // namespace pg
+
+extern "C" int pg_row_grid(int32_t n_rows) { return pg::row_grid(n_rows); }
+
+extern "C" int pg_ln_relu_fwd(const void* y, int64_t ldy, const float* gamma, const float* beta, float eps, int relu,
+                              void* out, int64_t ldo, float* mean, float* rstd, int32_t n_rows, int32_t d, int dtype,
+                              void* stream) {
+  using namespace pg;
+  PG_REQUIRE(y && gamma && beta && out && mean && rstd, "pg_ln_relu_fwd: null argument");
+  const int v = 16 / elem_size(dtype);
+  PG_REQUIRE(d > 0 && d % v == 0 && d / v <= 32 * kMaxVec, "pg_ln_relu_fwd: d=%d must be a multiple of %d and <= %d", d, v, 32 * kMaxVec * v);
+  PG_REQUIRE(vec_bytes(y, ldy, elem_size(dtype)) == 16 && vec_bytes(out, ldo, elem_size(dtype)) == 16, "pg_ln_relu_fwd: rows must be 16-byte aligned");
+  if (n_rows == 0) return PG_OK;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int grid = row_grid(n_rows);
+  if (dtype == PG_F32)
+    ln_relu_fwd_kernel<float><<<grid, kRowThreads, 0, st>>>(static_cast<const float*>(y), ldy, gamma, beta, eps, relu, static_cast<float*>(out), ldo, mean, rstd, n_rows, d);
+  else
+    ln_relu_fwd_kernel<__nv_bfloat16><<<grid, kRowThreads, 0, st>>>(static_cast<const __nv_bfloat16*>(y), ldy, gamma, beta, eps, relu, static_cast<__nv_bfloat16*>(out), ldo, mean, rstd, n_rows, d);
+  PG_LAUNCH_CHECK();
+  return PG_OK;
+}
+
+extern "C" int pg_ln_relu_bwd(const void* g_out, int64_t ldg, const void* out, int64_t ldo, const void* y, int64_t ldy,
+                              const float* mean, const float* rstd, const float* gamma, int relu, void* g_y,
+                              int64_t ldgy, float* dgamma, float* dbeta, float* colsum, float* partial,
+                              int32_t n_rows, int32_t d, int dtype, void* stream) {
+  using namespace pg;
+  PG_REQUIRE(g_out && y && mean && rstd && gamma && g_y && partial, "pg_ln_relu_bwd: null argument");
+  PG_REQUIRE(!relu || out, "pg_ln_relu_bwd: relu needs the forward output");
+  const int es = elem_size(dtype), v = 16 / es;
+  PG_REQUIRE(d > 0 && d % v == 0 && d / v <= 32 * kMaxVec, "pg_ln_relu_bwd: unsupported d=%d", d);
+  PG_REQUIRE(vec_bytes(g_out, ldg, es) == 16 && vec_bytes(y, ldy, es) == 16 && vec_bytes(g_y, ldgy, es) == 16 &&
+             (!relu || vec_bytes(out, ldo, es) == 16), "pg_ln_relu_bwd: rows must be 16-byte aligned");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int grid = row_grid(n_rows);
+  const size_t smem = 3 * static_cast<size_t>(d) * sizeof(float);
+  if (dtype == PG_F32)
+    ln_relu_bwd_kernel<float><<<grid, kRowThreads, smem, st>>>(static_cast<const float*>(g_out), ldg, static_cast<const float*>(out), ldo, static_cast<const float*>(y), ldy, mean, rstd, gamma, relu, static_cast<float*>(g_y), ldgy, partial, n_rows, d);
+  else
+    ln_relu_bwd_kernel<__nv_bfloat16><<<grid, kRowThreads, smem, st>>>(static_cast<const __nv_bfloat16*>(g_out), ldg, static_cast<const __nv_bfloat16*>(out), ldo, static_cast<const __nv_bfloat16*>(y), ldy, mean, rstd, gamma, relu, static_cast<__nv_bfloat16*>(g_y), ldgy, partial, n_rows, d);
+  PG_LAUNCH_CHECK();
+  colsum_final_kernel<<<(3 * d + 255) / 256, 256, 0, st>>>(partial, grid, 3 * d, dgamma, dbeta, colsum, d);
+  PG_LAUNCH_CHECK();
+  return PG_OK;
+}
+
+extern "C" int pg_ce_fwd(const void* z, int64_t ld, const int64_t* labels, int32_t n_rows, int32_t c, int dtype,
+                         float* lse, float* partial, float* loss, void* stream) {
+  using namespace pg;
+  PG_REQUIRE(z && labels && lse && partial && loss && c > 0, "pg_ce_fwd: bad argument");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int grid = row_grid(n_rows);
+  if (dtype == PG_F32) ce_fwd_kernel<float><<<grid, kRowThreads, 0, st>>>(static_cast<const float*>(z), ld, labels, n_rows, c, lse, partial);
+  else ce_fwd_kernel<__nv_bfloat16><<<grid, kRowThreads, 0, st>>>(static_cast<const __nv_bfloat16*>(z), ld, labels, n_rows, c, lse, partial);
+  PG_LAUNCH_CHECK();
+  colsum_final_kernel<<<1, 32, 0, st>>>(partial, grid, 1, loss, nullptr, nullptr, 1);
+  PG_LAUNCH_CHECK();
+  return PG_OK;
+}
+
+extern "C" int pg_ce_bwd(const void* z, int64_t ld, const int64_t* labels, const float* lse, const float* upstream,
+                         int32_t n_rows, int32_t n_total, int32_t c, int dtype, void* g, int64_t ldg, float* colsum,
+                         float* partial, void* stream) {
+  using namespace pg;
+  PG_REQUIRE(z && labels && lse && g && partial && c > 0 && n_total >= n_rows, "pg_ce_bwd: bad argument");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int grid = row_grid(n_total);
+  const size_t smem = static_cast<size_t>(c) * sizeof(float);
+  if (dtype == PG_F32) ce_bwd_kernel<float><<<grid, kRowThreads, smem, st>>>(static_cast<const float*>(z), ld, labels, lse, upstream, n_rows, n_total, c, static_cast<float*>(g), ldg, partial);
+  else ce_bwd_kernel<__nv_bfloat16><<<grid, kRowThreads, smem, st>>>(static_cast<const __nv_bfloat16*>(z), ld, labels, lse, upstream, n_rows, n_total, c, static_cast<__nv_bfloat16*>(g), ldg, partial);
+  PG_LAUNCH_CHECK();
+  if (colsum != nullptr) {
+    colsum_final_kernel<<<(c + 255) / 256, 256, 0, st>>>(partial, grid, c, colsum, nullptr, nullptr, c);
+    PG_LAUNCH_CHECK();
+  }
+  return PG_OK;
+}

@@ -184,6 +184,7 @@ class Buffer(object):
         self._counters = torch.zeros(max(1, 4 * L * size * self._nver), dtype=torch.int32, device=dev)
         self._status = torch.zeros(1, dtype=torch.int32, device=dev)
         self._comm_stream = torch.cuda.Stream(device=dev) if dev.type == 'cuda' else None
+        self._push_done = {}
         self._keep = []
 
         w.publish('pipegcn.buffer', {
@@ -244,6 +245,28 @@ class Buffer(object):
                 self._wait[(l, direction)] = torch.tensor(ptrs, dtype=torch.int64, device=dev) if ptrs else None
         self._connected = True
 
+    # ------------------------------------------------------------------ zero-copy producer interface
+    def _use_version(self) -> int:
+        return (self._epoch + 1) % 2 if self._pipeline else 0
+
+    def inner_view(self, layer):
+        """[N_in, d] view of the rows `update(layer, .)` will return first in this epoch.  A producer that writes
+        its output here (the LayerNorm/ReLU epilogue of the previous layer, the input features) saves `update`
+        the copy of the inner rows: the `torch.cat` of feature_buffer.py:132-141 costs nothing at all."""
+        if not self._ready or (layer, 0) not in self._f_off:
+            return None
+        v = self._use_version()
+        ev = self._push_done.get((layer, v))
+        if ev is not None:                       # the side-stream push of two epochs ago read these rows
+            torch.cuda.current_stream().wait_event(ev)
+        return self._f_buf[(layer, v)][:self._num_in, :self._layer_size[layer]]
+
+    def load_inner(self, layer, feat):
+        """Write `feat` into the inner rows of every version of layer `layer` (static input features)."""
+        d = self._layer_size[layer]
+        for v in range(self._nver):
+            self._f_buf[(layer, v)][:self._num_in, :d].copy_(feat)
+
     # ------------------------------------------------------------------ epoch control
     def next_epoch(self):
         self._epoch += 1
@@ -302,15 +325,20 @@ class Buffer(object):
         t = self._epoch
         if feat.stride(1) != 1:
             feat = feat.contiguous()
+        def aliased(v):
+            return feat.data_ptr() == self._f_buf[(layer, v)].data_ptr() and feat.stride(0) == self._ld[layer]
         if not self._pipeline:
             v = 0
-            self._push(self._self_msgs[(layer, v)], feat, d, 0)
+            if not aliased(v):
+                self._push(self._self_msgs[(layer, v)], feat, d, 0)
             self._push(self._fwd_msgs[(layer, v)], feat, d, t + 1)
             self._wait_flags(layer, 0, t + 1, f'forward_{layer}')
         else:
             v_use, v_send = (t + 1) % 2, t % 2
             v = v_use
-            self._push(self._self_msgs[(layer, v_use)], feat, d, 0)
+            zero_copy = aliased(v_use)
+            if not zero_copy:
+                self._push(self._self_msgs[(layer, v_use)], feat, d, 0)
             if t > 0:
                 self._wait_flags(layer, 0, t, f'forward_{layer}')
             ms = self._fwd_msgs[(layer, v_send)]
@@ -321,6 +349,10 @@ class Buffer(object):
                 self._keep.append(feat)
                 with torch.cuda.stream(self._comm_stream):
                     self._push(ms, feat, d, t + 1)
+                    if zero_copy:
+                        ev = torch.cuda.Event()
+                        ev.record()
+                        self._push_done[(layer, v_use)] = ev
         return self._f_buf[(layer, v)][:, :d]
 
     # ------------------------------------------------------------------ backward

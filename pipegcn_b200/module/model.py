@@ -58,9 +58,13 @@ class GraphSAGE(GNNBase):
     def _buffer(self):
         return self.buffer if self.buffer is not None else ctx.buffer
 
-    def _norm_act(self, i, h):
+    def _norm_act(self, i, h, dest=None):
         if self.use_norm:
             n = self.norm[i]
+            from .. import ops
+            if isinstance(n, nn.LayerNorm) and self.activation in (F.relu, torch.relu) and ops.ln_relu_supported(h):
+                # LayerNorm + ReLU in one pass, written straight into the next layer's exchange buffer
+                return ops.layer_norm_relu(h, n.weight, n.bias, n.eps, relu=True, out=dest)
             if isinstance(n, nn.LayerNorm) and h.dtype != n.weight.dtype:
                 h = F.layer_norm(h, n.normalized_shape, n.weight.to(h.dtype), n.bias.to(h.dtype), n.eps)
             else:
@@ -78,7 +82,10 @@ class GraphSAGE(GNNBase):
                 from .. import ops
                 h = ops.linear(self.dropout(h), layer.weight, layer.bias)
             if i < self.n_layers - 1:
-                h = self._norm_act(i, h)
+                dest = None
+                if self.training and i + 1 < self.n_graph_layers:
+                    dest = self._buffer().inner_view(i + 1)
+                h = self._norm_act(i, h, dest)
         return h
 
 

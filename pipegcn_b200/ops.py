@@ -198,10 +198,11 @@ class _Linear(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g):
         x, weight = ctx.saved_tensors
+        colsum = _take_colsum(g)
         g = _tma_ready(g if g.dtype == x.dtype else g.to(x.dtype))
         gx = gemm_nt(g, padded_weight(weight, x.dtype, transpose=True)) if ctx.needs_input_grad[0] else None
         gw = _mm_f32(g.t(), x).to(weight.dtype)
-        gb = g.float().sum(0) if ctx.has_bias else None
+        gb = (colsum if colsum is not None else g.float().sum(0)) if ctx.has_bias else None
         return gx, gw, gb
 
 
@@ -242,6 +243,7 @@ class SageLayerFn(torch.autograd.Function):
     def backward(ctx, g):
         x, ah, w1, w2 = ctx.saved_tensors
         graph, deg_f = ctx.graph, ctx.deg_f
+        colsum = _take_colsum(g)
         g = _tma_ready(g if g.dtype == x.dtype else g.to(x.dtype))
         g_feat = None
         if ctx.needs_input_grad[0]:
@@ -253,7 +255,7 @@ class SageLayerFn(torch.autograd.Function):
         gt = g.t()
         gw1 = _mm_f32(gt, x).to(w1.dtype)
         gw2 = _mm_f32(gt, ah).to(w2.dtype)
-        gb = g.float().sum(0) if ctx.has_bias else None
+        gb = (colsum if colsum is not None else g.float().sum(0)) if ctx.has_bias else None
         return g_feat, None, None, gw1, gb, gw2, gb
 
 
@@ -264,3 +266,113 @@ def sage_layer(feat, graph, deg_f, w1, b1, w2, b2) -> torch.Tensor:
 def sage_linear(x, ah, w1, b1, w2, b2) -> torch.Tensor:
     """x @ W1^T + b1 + ah @ W2^T + b2   (layer.py:51) -- un-fused composition (eval branch)."""
     return linear(x, w1, b1) + linear(ah, w2, b2)
+
+
+# ---- row-wise epilogues (csrc/rowops.cu) -------------------------------------------------------------------
+# column sums of a gradient tensor computed as a by-product by the kernel that produced it, keyed by the
+# tensor's address: the bias gradient of the linear upstream (saves a full pass over [N, d])
+_COLSUM = {}
+
+
+def _stash_colsum(t: torch.Tensor, colsum: torch.Tensor):
+    if len(_COLSUM) > 64:
+        _COLSUM.clear()
+    _COLSUM[(t.data_ptr(), tuple(t.shape))] = colsum
+
+
+def _take_colsum(t: torch.Tensor):
+    return _COLSUM.pop((t.data_ptr(), tuple(t.shape)), None)
+
+
+def ln_relu_supported(y: torch.Tensor) -> bool:
+    v = 16 // y.element_size()
+    d = y.shape[1]
+    return y.is_cuda and y.dim() == 2 and d % v == 0 and d // v <= 128 and y.stride(1) == 1 \
+        and (y.stride(0) * y.element_size()) % 16 == 0 and y.data_ptr() % 16 == 0
+
+
+class LayerNormReLU(torch.autograd.Function):
+    """relu(LayerNorm(y)) in one pass (model.py:53-56); the backward also yields d gamma, d beta and the column
+    sums of g_y, which is the bias gradient of the linear that produced y."""
+
+    @staticmethod
+    def forward(ctx, y, gamma, beta, eps, relu, out):
+        n, d = y.shape
+        if out is None:
+            out = alloc_rows(n, d, y.dtype, y.device)
+        mean = torch.empty(n, dtype=torch.float32, device=y.device)
+        rstd = torch.empty(n, dtype=torch.float32, device=y.device)
+        g32, b32 = gamma.detach().float().contiguous(), beta.detach().float().contiguous()
+        _C.count()
+        _C.check(_C.lib.pg_ln_relu_fwd(y.data_ptr(), y.stride(0), g32.data_ptr(), b32.data_ptr(), float(eps), int(relu),
+                                       out.data_ptr(), out.stride(0), mean.data_ptr(), rstd.data_ptr(), n, d,
+                                       _C.dtype_code(y.dtype), _C.stream_ptr()), "pg_ln_relu_fwd")
+        ctx.save_for_backward(y, out, mean, rstd, g32)
+        ctx.relu = bool(relu)
+        ctx.param_dtype = gamma.dtype
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        y, out, mean, rstd, g32 = ctx.saved_tensors
+        n, d = y.shape
+        if g.dtype != y.dtype or g.stride(1) != 1 or (g.stride(0) * g.element_size()) % 16 or g.data_ptr() % 16:
+            g = _tma_ready(g.to(y.dtype))
+        g_y = alloc_rows(n, d, y.dtype, y.device)
+        grid = _C.lib.pg_row_grid(n)
+        partial = torch.empty(grid * 3 * d, dtype=torch.float32, device=y.device)
+        red = torch.empty(3, d, dtype=torch.float32, device=y.device)
+        _C.count(2)
+        _C.check(_C.lib.pg_ln_relu_bwd(g.data_ptr(), g.stride(0), out.data_ptr(), out.stride(0), y.data_ptr(), y.stride(0),
+                                       mean.data_ptr(), rstd.data_ptr(), g32.data_ptr(), int(ctx.relu),
+                                       g_y.data_ptr(), g_y.stride(0), red[0].data_ptr(), red[1].data_ptr(),
+                                       red[2].data_ptr(), partial.data_ptr(), n, d, _C.dtype_code(y.dtype),
+                                       _C.stream_ptr()), "pg_ln_relu_bwd")
+        _stash_colsum(g_y, red[2])
+        return g_y, red[0].to(ctx.param_dtype), red[1].to(ctx.param_dtype), None, None, None
+
+
+def layer_norm_relu(y, gamma, beta, eps=1e-5, relu=True, out=None):
+    return LayerNormReLU.apply(y, gamma, beta, eps, relu, out)
+
+
+class CrossEntropySum(torch.autograd.Function):
+    """CrossEntropyLoss(reduction='sum') over the first n_train rows of the logits (train.py:320,351); the gradient
+    is zero on the remaining rows (train rows come first after move_train_first)."""
+
+    @staticmethod
+    def forward(ctx, logits, labels, n_train):
+        n, c = logits.shape
+        dev = logits.device
+        lse = torch.empty(max(n_train, 1), dtype=torch.float32, device=dev)
+        grid = _C.lib.pg_row_grid(max(n, 1))
+        partial = torch.empty(grid * max(c, 1), dtype=torch.float32, device=dev)
+        loss = torch.zeros(1, dtype=torch.float32, device=dev)
+        if n_train:
+            _C.count(2)
+            _C.check(_C.lib.pg_ce_fwd(logits.data_ptr(), logits.stride(0), labels.data_ptr(), n_train, c,
+                                      _C.dtype_code(logits.dtype), lse.data_ptr(), partial.data_ptr(), loss.data_ptr(),
+                                      _C.stream_ptr()), "pg_ce_fwd")
+        ctx.save_for_backward(logits, labels, lse, partial)
+        ctx.n_train = n_train
+        return loss[0]
+
+    @staticmethod
+    def backward(ctx, up):
+        logits, labels, lse, partial = ctx.saved_tensors
+        n, c = logits.shape
+        g = alloc_rows(n, c, logits.dtype, logits.device)
+        colsum = torch.empty(c, dtype=torch.float32, device=logits.device)
+        up = up.detach().float().reshape(1).contiguous()
+        _C.count(2)
+        _C.check(_C.lib.pg_ce_bwd(logits.data_ptr(), logits.stride(0), labels.data_ptr(), lse.data_ptr(), up.data_ptr(),
+                                  ctx.n_train, n, c, _C.dtype_code(logits.dtype), g.data_ptr(), g.stride(0),
+                                  colsum.data_ptr(), partial.data_ptr(), _C.stream_ptr()), "pg_ce_bwd")
+        _stash_colsum(g, colsum)
+        return g, None, None
+
+
+def cross_entropy_sum(logits, labels, n_train):
+    if logits.stride(1) != 1:
+        logits = logits.contiguous()
+    return CrossEntropySum.apply(logits, labels, int(n_train))

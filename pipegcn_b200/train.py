@@ -70,6 +70,8 @@ class RankEngine:
         if args.use_pp:
             raise NotImplementedError("--use-pp precompute is scheduled after the core path (SURVEY.md §8f-2)")
         self.feat = layout.feat.to(dev).to(self.dtype)
+        # the static input features live in the exchange buffer of layer 0 (all versions): update(0, .) copies nothing
+        self.buffer.load_inner(0, self.feat)
         tm = layout.train_mask.to(dev)
         self.part_train = int(tm.sum().item())
         prefix = bool(tm[:self.part_train].all().item()) if self.part_train else True
@@ -92,13 +94,23 @@ class RankEngine:
     def forward_backward(self, keep_logits=False):
         """train.py:343-355; returns the summed loss (device tensor, no host sync)."""
         self.model.train()
-        logits = self.model(self.graph, self.feat, self.in_deg)
-        loss = self.loss_fcn(logits[self.train_sel].float(), self.labels)
+        feat = self.buffer.inner_view(0)
+        logits = self.model(self.graph, feat if feat is not None else self.feat, self.in_deg)
+        if isinstance(self.train_sel, slice) and logits.dtype in (torch.float32, torch.bfloat16):
+            from . import ops
+            loss = ops.cross_entropy_sum(logits, self.labels, self.part_train)      # fused softmax-CE (sum)
+        else:
+            loss = self.loss_fcn(logits[self.train_sel].float(), self.labels)
         if keep_logits:
             self.last_logits = logits.detach()
         self.optimizer.zero_grad(set_to_none=True)
         loss.backward()
         return loss.detach()
+
+    def set_features(self, feat):
+        """New input features for the coming epoch (host or device tensor, [N_in, n_feat])."""
+        view = self.buffer.inner_view(0)
+        (view if view is not None else self.feat).copy_(feat, non_blocking=True)
 
     def finish_epoch(self, reduce=True):
         """train.py:357-362."""

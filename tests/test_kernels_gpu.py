@@ -175,3 +175,51 @@ def test_sage_layer_fn_matches_torch():
     want = [ref.detach()] + [t.grad for t in (feat, w1, b1, w2, b2)]
     for a, b in zip(got, want):
         assert (a - b).abs().max().item() <= 1e-4 * b.abs().max().item() + 1e-5     # 3xTF32 tensor-core product
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("d", [16, 256, 600])
+def test_layer_norm_relu_matches_torch(dtype, d):
+    from pipegcn_b200 import ops
+    from pipegcn_b200.graph import alloc_rows
+    n = 3000
+    torch.manual_seed(d)
+    y = alloc_rows(n, d, dtype, DEV)
+    y.copy_(torch.randn(n, d, device=DEV) * 2 + 0.5)
+    gamma = (torch.rand(d, device=DEV) + 0.5).requires_grad_(True)
+    beta = torch.randn(d, device=DEV).requires_grad_(True)
+    go = torch.randn(n, d, device=DEV).to(dtype)
+    yq = y.detach().clone().requires_grad_(True)
+    assert ops.ln_relu_supported(yq)
+    out = ops.layer_norm_relu(yq, gamma, beta, 1e-5, relu=True)
+    out.backward(go)
+    got = [out.detach().float(), yq.grad.float(), gamma.grad.clone(), beta.grad.clone()]
+    colsum = ops._take_colsum(yq.grad)
+    gamma.grad = beta.grad = None
+    yr = y.detach().float().clone().requires_grad_(True)
+    ref = torch.relu(torch.nn.functional.layer_norm(yr, (d,), gamma, beta, 1e-5))
+    ref.backward(go.float())
+    want = [ref.detach(), yr.grad, gamma.grad, beta.grad]
+    tol = 1e-4 if dtype == torch.float32 else 2e-2
+    for a, b in zip(got, want):
+        assert (a - b).abs().max().item() <= tol * max(b.abs().max().item(), 1.0)
+    assert colsum is not None
+    assert (colsum - got[1].sum(0)).abs().max().item() <= 1e-3 * max(got[1].sum(0).abs().max().item(), 1.0)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_cross_entropy_sum_matches_torch(dtype):
+    from pipegcn_b200 import ops
+    n, n_train, c = 5000, 3211, 41
+    torch.manual_seed(1)
+    z = (torch.randn(n, c, device=DEV) * 3).to(dtype).requires_grad_(True)
+    labels = torch.randint(0, c, (n_train,), device=DEV)
+    loss = ops.cross_entropy_sum(z, labels, n_train)
+    (loss * 0.5).backward()
+    zr = z.detach().float().requires_grad_(True)
+    ref = torch.nn.functional.cross_entropy(zr[:n_train], labels, reduction="sum")
+    (ref * 0.5).backward()
+    assert abs(loss.item() - ref.item()) <= 1e-5 * abs(ref.item())
+    tol = 1e-5 if dtype == torch.float32 else 1e-2
+    assert (z.grad.float() - zr.grad).abs().max().item() <= tol
+    assert torch.count_nonzero(z.grad[n_train:]) == 0
