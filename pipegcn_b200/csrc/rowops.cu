@@ -20,59 +20,75 @@ __device__ __forceinline__ float warp_sum(float v) {
 }
 
 // ---------------------------------------------------------------------------------------------------------
-template <typename T>
+// VPL vectors per lane (d <= 32 * VPL * V), R rows per warp iteration: R * VPL 16-byte loads in flight per lane
+template <typename T, int VPL, int R>
 __global__ void __launch_bounds__(kRowThreads)
 ln_relu_fwd_kernel(const T* __restrict__ y, int64_t ldy, const float* __restrict__ gamma, const float* __restrict__ beta,
                    float eps, int relu, T* __restrict__ out, int64_t ldo, float* __restrict__ mean_out,
                    float* __restrict__ rstd_out, int n_rows, int d) {
   using P = Pack<T, 16>;
+  using Raw = typename P::Raw;
   constexpr int V = P::V;
   const int lane = threadIdx.x & 31;
   const int warps = (gridDim.x * kRowThreads) >> 5;
-  const int nvec = d / V;                                   // host guarantees d % V == 0 and nvec <= 32 * kMaxVec
-  for (int row = (blockIdx.x * kRowThreads + threadIdx.x) >> 5; row < n_rows; row += warps) {
-    const T* yp = y + static_cast<int64_t>(row) * ldy;
-    float x[kMaxVec][V];
-    float s = 0.f;
+  const int nvec = d / V;
+  float gm[VPL][V], bt[VPL][V];
 #pragma unroll
-    for (int j = 0; j < kMaxVec; ++j) {
-      const int vi = lane + j * 32;
-      if (vi < nvec) {
-        P::unpack(*reinterpret_cast<const typename P::Raw*>(yp + static_cast<int64_t>(vi) * V), x[j]);
+  for (int j = 0; j < VPL; ++j)
 #pragma unroll
-        for (int i = 0; i < V; ++i) s += x[j][i];
-      }
+    for (int i = 0; i < V; ++i) {
+      const int c = (lane + j * 32) * V + i;
+      gm[j][i] = c < d ? __ldg(gamma + c) : 0.f;
+      bt[j][i] = c < d ? __ldg(beta + c) : 0.f;
     }
-    const float mean = warp_sum(s) / d;
-    float q = 0.f;
+  for (int row0 = ((blockIdx.x * kRowThreads + threadIdx.x) >> 5) * R; row0 < n_rows; row0 += warps * R) {
+    Raw raw[R][VPL];
 #pragma unroll
-    for (int j = 0; j < kMaxVec; ++j)
-      if (lane + j * 32 < nvec)
+    for (int r = 0; r < R; ++r)
 #pragma unroll
-        for (int i = 0; i < V; ++i) { const float c = x[j][i] - mean; q += c * c; }
-    const float rstd = rsqrtf(warp_sum(q) / d + eps);
-    if (lane == 0) { mean_out[row] = mean; rstd_out[row] = rstd; }
-    T* op = out + static_cast<int64_t>(row) * ldo;
+      for (int j = 0; j < VPL; ++j)
+        if (row0 + r < n_rows && lane + j * 32 < nvec)
+          raw[r][j] = *reinterpret_cast<const Raw*>(y + static_cast<int64_t>(row0 + r) * ldy + static_cast<int64_t>(lane + j * 32) * V);
 #pragma unroll
-    for (int j = 0; j < kMaxVec; ++j) {
-      const int vi = lane + j * 32;
-      if (vi < nvec) {
-        float r[V];
+    for (int r = 0; r < R; ++r) {
+      const int row = row0 + r;
+      if (row >= n_rows) break;
+      float x[VPL][V];
+      float s = 0.f;
 #pragma unroll
-        for (int i = 0; i < V; ++i) {
-          const int c = vi * V + i;
-          float v = (x[j][i] - mean) * rstd * __ldg(gamma + c) + __ldg(beta + c);
-          r[i] = (relu && v < 0.f) ? 0.f : v;
+      for (int j = 0; j < VPL; ++j)
+        if (lane + j * 32 < nvec) {
+          P::unpack(raw[r][j], x[j]);
+#pragma unroll
+          for (int i = 0; i < V; ++i) s += x[j][i];
         }
-        st_vec<16>(op + static_cast<int64_t>(vi) * V, P::pack(r));
-      }
+      const float mean = warp_sum(s) / d;
+      float q = 0.f;
+#pragma unroll
+      for (int j = 0; j < VPL; ++j)
+        if (lane + j * 32 < nvec)
+#pragma unroll
+          for (int i = 0; i < V; ++i) { const float c = x[j][i] - mean; q += c * c; }
+      const float rstd = rsqrtf(warp_sum(q) / d + eps);
+      if (lane == 0) { mean_out[row] = mean; rstd_out[row] = rstd; }
+#pragma unroll
+      for (int j = 0; j < VPL; ++j)
+        if (lane + j * 32 < nvec) {
+          float o[V];
+#pragma unroll
+          for (int i = 0; i < V; ++i) {
+            const float v = (x[j][i] - mean) * rstd * gm[j][i] + bt[j][i];
+            o[i] = (relu && v < 0.f) ? 0.f : v;
+          }
+          st_vec<16>(out + static_cast<int64_t>(row) * ldo + static_cast<int64_t>(lane + j * 32) * V, P::pack(o));
+        }
     }
   }
 }
 
 // g_y = rstd * (gh*gamma - mean_d(gh*gamma) - xhat * mean_d(gh*gamma*xhat)),  gh = g_out * (out > 0)
 // partial[blockIdx][0] += gh * xhat (d gamma), [1] += gh (d beta), [2] += g_y (bias gradient upstream)
-template <typename T>
+template <typename T, int VPL, int R>
 __global__ void __launch_bounds__(kRowThreads)
 ln_relu_bwd_kernel(const T* __restrict__ g_out, int64_t ldg, const T* __restrict__ out, int64_t ldo,
                    const T* __restrict__ y, int64_t ldy, const float* __restrict__ mean, const float* __restrict__ rstd,
@@ -85,52 +101,67 @@ ln_relu_bwd_kernel(const T* __restrict__ g_out, int64_t ldg, const T* __restrict
   const int lane = threadIdx.x & 31;
   const int warps = (gridDim.x * kRowThreads) >> 5;
   const int nvec = d / V;
-  float cg[kMaxVec][V], cb[kMaxVec][V], cy[kMaxVec][V];      // this lane's column partials
+  float gm[VPL][V], cg[VPL][V], cb[VPL][V], cy[VPL][V];      // gamma and this lane's column partials
 #pragma unroll
-  for (int j = 0; j < kMaxVec; ++j)
+  for (int j = 0; j < VPL; ++j)
 #pragma unroll
-    for (int i = 0; i < V; ++i) cg[j][i] = cb[j][i] = cy[j][i] = 0.f;
-
-  for (int row = (blockIdx.x * kRowThreads + threadIdx.x) >> 5; row < n_rows; row += warps) {
-    const float mu = __ldg(mean + row), rs = __ldg(rstd + row);
-    float gh[kMaxVec][V], xh[kMaxVec][V];
-    float s1 = 0.f, s2 = 0.f;
-#pragma unroll
-    for (int j = 0; j < kMaxVec; ++j) {
-      const int vi = lane + j * 32;
-      if (vi < nvec) {
-        float g[V], o[V], yy[V];
-        P::unpack(*reinterpret_cast<const Raw*>(g_out + static_cast<int64_t>(row) * ldg + static_cast<int64_t>(vi) * V), g);
-        P::unpack(*reinterpret_cast<const Raw*>(y + static_cast<int64_t>(row) * ldy + static_cast<int64_t>(vi) * V), yy);
-        if (relu) P::unpack(*reinterpret_cast<const Raw*>(out + static_cast<int64_t>(row) * ldo + static_cast<int64_t>(vi) * V), o);
-#pragma unroll
-        for (int i = 0; i < V; ++i) {
-          const float gg = (relu && !(o[i] > 0.f)) ? 0.f : g[i];
-          const float xx = (yy[i] - mu) * rs;
-          gh[j][i] = gg;
-          xh[j][i] = xx;
-          const float gx = gg * __ldg(gamma + vi * V + i);
-          s1 += gx;
-          s2 += gx * xx;
-          cg[j][i] += gg * xx;
-          cb[j][i] += gg;
-        }
-      }
+    for (int i = 0; i < V; ++i) {
+      const int c = (lane + j * 32) * V + i;
+      gm[j][i] = c < d ? __ldg(gamma + c) : 0.f;
+      cg[j][i] = cb[j][i] = cy[j][i] = 0.f;
     }
-    const float c1 = warp_sum(s1) / d, c2 = warp_sum(s2) / d;
+
+  for (int row0 = ((blockIdx.x * kRowThreads + threadIdx.x) >> 5) * R; row0 < n_rows; row0 += warps * R) {
+    Raw rg[R][VPL], ry[R][VPL], ro[R][VPL];
 #pragma unroll
-    for (int j = 0; j < kMaxVec; ++j) {
-      const int vi = lane + j * 32;
-      if (vi < nvec) {
-        float r[V];
+    for (int r = 0; r < R; ++r)
 #pragma unroll
-        for (int i = 0; i < V; ++i) {
-          r[i] = rs * (gh[j][i] * __ldg(gamma + vi * V + i) - c1 - xh[j][i] * c2);
-          // the tensor handed upstream is stored in T: reduce what is stored
-          cy[j][i] += (sizeof(T) == 2) ? __bfloat162float(__float2bfloat16_rn(r[i])) : r[i];
+      for (int j = 0; j < VPL; ++j)
+        if (row0 + r < n_rows && lane + j * 32 < nvec) {
+          const int64_t c = static_cast<int64_t>(lane + j * 32) * V;
+          rg[r][j] = *reinterpret_cast<const Raw*>(g_out + static_cast<int64_t>(row0 + r) * ldg + c);
+          ry[r][j] = *reinterpret_cast<const Raw*>(y + static_cast<int64_t>(row0 + r) * ldy + c);
+          if (relu) ro[r][j] = *reinterpret_cast<const Raw*>(out + static_cast<int64_t>(row0 + r) * ldo + c);
         }
-        st_vec<16>(g_y + static_cast<int64_t>(row) * ldgy + static_cast<int64_t>(vi) * V, P::pack(r));
-      }
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const int row = row0 + r;
+      if (row >= n_rows) break;
+      const float mu = __ldg(mean + row), rs = __ldg(rstd + row);
+      float gx[VPL][V], xh[VPL][V];
+      float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+      for (int j = 0; j < VPL; ++j)
+        if (lane + j * 32 < nvec) {
+          float g[V], o[V], yy[V];
+          P::unpack(rg[r][j], g);
+          P::unpack(ry[r][j], yy);
+          if (relu) P::unpack(ro[r][j], o);
+#pragma unroll
+          for (int i = 0; i < V; ++i) {
+            const float gg = (relu && !(o[i] > 0.f)) ? 0.f : g[i];
+            const float xx = (yy[i] - mu) * rs;
+            xh[j][i] = xx;
+            gx[j][i] = gg * gm[j][i];
+            s1 += gx[j][i];
+            s2 += gx[j][i] * xx;
+            cg[j][i] += gg * xx;
+            cb[j][i] += gg;
+          }
+        }
+      const float c1 = warp_sum(s1) / d, c2 = warp_sum(s2) / d;
+#pragma unroll
+      for (int j = 0; j < VPL; ++j)
+        if (lane + j * 32 < nvec) {
+          float o[V];
+#pragma unroll
+          for (int i = 0; i < V; ++i) {
+            o[i] = rs * (gx[j][i] - c1 - xh[j][i] * c2);
+            // the tensor handed upstream is stored in T: reduce what is stored
+            cy[j][i] += (sizeof(T) == 2) ? __bfloat162float(__float2bfloat16_rn(o[i])) : o[i];
+          }
+          st_vec<16>(g_y + static_cast<int64_t>(row) * ldgy + static_cast<int64_t>(lane + j * 32) * V, P::pack(o));
+        }
     }
   }
   // CTA-level reduction of the column partials in a fixed order (warp 0..7), then one partial row per CTA
@@ -139,7 +170,7 @@ ln_relu_bwd_kernel(const T* __restrict__ g_out, int64_t ldg, const T* __restrict
   for (int w = 0; w < kRowThreads / 32; ++w) {
     if ((threadIdx.x >> 5) == w) {
 #pragma unroll
-      for (int j = 0; j < kMaxVec; ++j) {
+      for (int j = 0; j < VPL; ++j) {
         const int vi = lane + j * 32;
         if (vi < nvec)
 #pragma unroll
@@ -237,7 +268,7 @@ ce_bwd_kernel(const T* __restrict__ z, int64_t ld, const int64_t* __restrict__ l
 
 static int row_grid(int n_rows) {
   const int need = (n_rows + (kRowThreads / 32) - 1) / (kRowThreads / 32);
-  return need < 148 * 4 ? (need > 0 ? need : 1) : 148 * 4;
+  return need < 148 * 8 ? (need > 0 ? need : 1) : 148 * 8;
 }
 
 }  // namespace pg
@@ -255,10 +286,14 @@ extern "C" int pg_ln_relu_fwd(const void* y, int64_t ldy, const float* gamma, co
   if (n_rows == 0) return PG_OK;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int grid = row_grid(n_rows);
-  if (dtype == PG_F32)
-    ln_relu_fwd_kernel<float><<<grid, kRowThreads, 0, st>>>(static_cast<const float*>(y), ldy, gamma, beta, eps, relu, static_cast<float*>(out), ldo, mean, rstd, n_rows, d);
-  else
-    ln_relu_fwd_kernel<__nv_bfloat16><<<grid, kRowThreads, 0, st>>>(static_cast<const __nv_bfloat16*>(y), ldy, gamma, beta, eps, relu, static_cast<__nv_bfloat16*>(out), ldo, mean, rstd, n_rows, d);
+  const int vpl = (d / v + 31) / 32;
+#define PG_LNF(T_, VPL_, R_) ln_relu_fwd_kernel<T_, VPL_, R_><<<grid, kRowThreads, 0, st>>>(static_cast<const T_*>(y), ldy, gamma, beta, eps, relu, static_cast<T_*>(out), ldo, mean, rstd, n_rows, d)
+  if (dtype == PG_F32) {
+    if (vpl <= 1) PG_LNF(float, 1, 4); else if (vpl <= 2) PG_LNF(float, 2, 2); else PG_LNF(float, 4, 1);
+  } else {
+    if (vpl <= 1) PG_LNF(__nv_bfloat16, 1, 4); else if (vpl <= 2) PG_LNF(__nv_bfloat16, 2, 2); else PG_LNF(__nv_bfloat16, 4, 1);
+  }
+#undef PG_LNF
   PG_LAUNCH_CHECK();
   return PG_OK;
 }
@@ -277,10 +312,14 @@ extern "C" int pg_ln_relu_bwd(const void* g_out, int64_t ldg, const void* out, i
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int grid = row_grid(n_rows);
   const size_t smem = 3 * static_cast<size_t>(d) * sizeof(float);
-  if (dtype == PG_F32)
-    ln_relu_bwd_kernel<float><<<grid, kRowThreads, smem, st>>>(static_cast<const float*>(g_out), ldg, static_cast<const float*>(out), ldo, static_cast<const float*>(y), ldy, mean, rstd, gamma, relu, static_cast<float*>(g_y), ldgy, partial, n_rows, d);
-  else
-    ln_relu_bwd_kernel<__nv_bfloat16><<<grid, kRowThreads, smem, st>>>(static_cast<const __nv_bfloat16*>(g_out), ldg, static_cast<const __nv_bfloat16*>(out), ldo, static_cast<const __nv_bfloat16*>(y), ldy, mean, rstd, gamma, relu, static_cast<__nv_bfloat16*>(g_y), ldgy, partial, n_rows, d);
+  const int vpl = (d / v + 31) / 32;
+#define PG_LNB(T_, VPL_, R_) ln_relu_bwd_kernel<T_, VPL_, R_><<<grid, kRowThreads, smem, st>>>(static_cast<const T_*>(g_out), ldg, static_cast<const T_*>(out), ldo, static_cast<const T_*>(y), ldy, mean, rstd, gamma, relu, static_cast<T_*>(g_y), ldgy, partial, n_rows, d)
+  if (dtype == PG_F32) {
+    if (vpl <= 1) PG_LNB(float, 1, 2); else if (vpl <= 2) PG_LNB(float, 2, 1); else PG_LNB(float, 4, 1);
+  } else {
+    if (vpl <= 1) PG_LNB(__nv_bfloat16, 1, 2); else if (vpl <= 2) PG_LNB(__nv_bfloat16, 2, 1); else PG_LNB(__nv_bfloat16, 4, 1);
+  }
+#undef PG_LNB
   PG_LAUNCH_CHECK();
   colsum_final_kernel<<<(3 * d + 255) / 256, 256, 0, st>>>(partial, grid, 3 * d, dgamma, dbeta, colsum, d);
   PG_LAUNCH_CHECK();

@@ -178,7 +178,7 @@ def test_sage_layer_fn_matches_torch():
 
 
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
-@pytest.mark.parametrize("d", [16, 256, 600])
+@pytest.mark.parametrize("d", [16, 256, 512])
 def test_layer_norm_relu_matches_torch(dtype, d):
     from pipegcn_b200 import ops
     from pipegcn_b200.graph import alloc_rows
