@@ -111,6 +111,10 @@ int pg_split_tf32(const float* x, int64_t ldx, float* hi, float* lo, int64_t ld,
  * pg_row_grid(n_rows) * 3 * d floats for the LayerNorm backward, pg_row_grid(n) * max(c, 1) for the loss).
  * ---------------------------------------------------------------------------------------- */
 int pg_row_grid(int32_t n_rows);
+/* out = keep ? x / (1 - p) : 0 with keep a pure function of (seed, element index) -- the backward calls it again on
+ * the gradient with the same seed instead of storing a mask (dropout of model.py:47; in place allowed) */
+int pg_dropout(const void* x, int64_t ldx, void* out, int64_t ldo, int32_t n_rows, int32_t d, int dtype, float p,
+               uint64_t seed, void* stream);
 /* out = relu?(LayerNorm(y) * gamma + beta), mean/rstd [n_rows] kept for the backward; d % (16/elem) == 0 */
 int pg_ln_relu_fwd(const void* y, int64_t ldy, const float* gamma, const float* beta, float eps, int relu,
                    void* out, int64_t ldo, float* mean, float* rstd, int32_t n_rows, int32_t d, int dtype,

@@ -188,15 +188,16 @@ ln_relu_bwd_kernel(const T* __restrict__ g_out, int64_t ldg, const T* __restrict
   for (int i = threadIdx.x; i < 3 * d; i += kRowThreads) pp[i] = red[i];
 }
 
-// out[k] = sum over blocks of partial[b][k], in block order
+// out[k] = sum over blocks of partial[b][k]: one warp per column, lanes stride over the blocks, fixed order
 __global__ void colsum_final_kernel(const float* __restrict__ partial, int n_blocks, int width, float* __restrict__ out0,
                                     float* __restrict__ out1, float* __restrict__ out2, int d) {
-  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  const int k = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (k >= width) return;
   float s = 0.f;
-  for (int b = 0; b < n_blocks; ++b) s += partial[static_cast<int64_t>(b) * width + k];
+  for (int b = lane; b < n_blocks; b += 32) s += partial[static_cast<int64_t>(b) * width + k];
+  s = warp_sum(s);
   float* o = (k < d) ? out0 : (k < 2 * d ? out1 : out2);
-  if (o != nullptr) o[k % d] = s;
+  if (lane == 0 && o != nullptr) o[k % d] = s;
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -266,6 +267,36 @@ ce_bwd_kernel(const T* __restrict__ z, int64_t ld, const int64_t* __restrict__ l
   for (int i = threadIdx.x; i < c; i += kRowThreads) pp[i] = red[i];
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Dropout with a counter-based generator: keep(i) is a pure function of (seed, element index), so the backward
+// regenerates the mask instead of storing it.  out = keep ? x / (1 - p) : 0.  16 random bits per element.
+__device__ __forceinline__ uint32_t mix32(uint32_t x) {       // lowbias32 finaliser
+  x ^= x >> 16; x *= 0x7feb352dU; x ^= x >> 15; x *= 0x846ca68bU; x ^= x >> 16;
+  return x;
+}
+template <typename T>
+__global__ void __launch_bounds__(256)
+dropout_kernel(const T* __restrict__ x, int64_t ldx, T* __restrict__ out, int64_t ldo, int n_rows, int nvec,
+               uint32_t thresh16, float scale, uint32_t seed_lo, uint32_t seed_hi) {
+  using P = Pack<T, 16>;
+  constexpr int V = P::V;
+  const int64_t total = static_cast<int64_t>(n_rows) * nvec;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int r = static_cast<int>(i / nvec), vi = static_cast<int>(i % nvec);
+    float f[V];
+    P::unpack(*reinterpret_cast<const typename P::Raw*>(x + static_cast<int64_t>(r) * ldx + static_cast<int64_t>(vi) * V), f);
+    const uint32_t base = mix32(static_cast<uint32_t>(i) ^ seed_lo) ^ mix32(static_cast<uint32_t>(i >> 32) + seed_hi);
+#pragma unroll
+    for (int k = 0; k < V; k += 2) {
+      const uint32_t h = mix32(base + 0x9e3779b9U * (k / 2 + 1));
+      f[k] = ((h & 0xffffU) >= thresh16) ? f[k] * scale : 0.f;
+      if (k + 1 < V) f[k + 1] = ((h >> 16) >= thresh16) ? f[k + 1] * scale : 0.f;
+    }
+    st_vec<16>(out + static_cast<int64_t>(r) * ldo + static_cast<int64_t>(vi) * V, P::pack(f));
+  }
+}
+
 static int row_grid(int n_rows) {
   const int need = (n_rows + (kRowThreads / 32) - 1) / (kRowThreads / 32);
   return need < 148 * 8 ? (need > 0 ? need : 1) : 148 * 8;
@@ -274,6 +305,28 @@ static int row_grid(int n_rows) {
 }  // namespace pg
 
 extern "C" int pg_row_grid(int32_t n_rows) { return pg::row_grid(n_rows); }
+
+extern "C" int pg_dropout(const void* x, int64_t ldx, void* out, int64_t ldo, int32_t n_rows, int32_t d, int dtype,
+                          float p, uint64_t seed, void* stream) {
+  using namespace pg;
+  PG_REQUIRE(x && out && p >= 0.f && p < 1.f, "pg_dropout: bad argument");
+  const int es = elem_size(dtype), v = 16 / es;
+  PG_REQUIRE(d > 0 && round_up(d, v) <= ldx && round_up(d, v) <= ldo && vec_bytes(x, ldx, es) == 16 && vec_bytes(out, ldo, es) == 16,
+             "pg_dropout: rows must be 16-byte aligned and padded to the vector width");
+  const int nvec = static_cast<int>(round_up(d, v) / v);
+  const int64_t total = static_cast<int64_t>(n_rows) * nvec;
+  if (total == 0) return PG_OK;
+  const unsigned blocks = static_cast<unsigned>((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
+  const uint32_t thresh = static_cast<uint32_t>(p * 65536.0f + 0.5f);
+  const float scale = 1.0f / (1.0f - p);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (dtype == PG_F32)
+    dropout_kernel<float><<<blocks, 256, 0, st>>>(static_cast<const float*>(x), ldx, static_cast<float*>(out), ldo, n_rows, nvec, thresh, scale, static_cast<uint32_t>(seed), static_cast<uint32_t>(seed >> 32));
+  else
+    dropout_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(x), ldx, static_cast<__nv_bfloat16*>(out), ldo, n_rows, nvec, thresh, scale, static_cast<uint32_t>(seed), static_cast<uint32_t>(seed >> 32));
+  PG_LAUNCH_CHECK();
+  return PG_OK;
+}
 
 extern "C" int pg_ln_relu_fwd(const void* y, int64_t ldy, const float* gamma, const float* beta, float eps, int relu,
                               void* out, int64_t ldo, float* mean, float* rstd, int32_t n_rows, int32_t d, int dtype,
@@ -321,7 +374,7 @@ extern "C" int pg_ln_relu_bwd(const void* g_out, int64_t ldg, const void* out, i
   }
 #undef PG_LNB
   PG_LAUNCH_CHECK();
-  colsum_final_kernel<<<(3 * d + 255) / 256, 256, 0, st>>>(partial, grid, 3 * d, dgamma, dbeta, colsum, d);
+  colsum_final_kernel<<<(3 * d * 32 + 255) / 256, 256, 0, st>>>(partial, grid, 3 * d, dgamma, dbeta, colsum, d);
   PG_LAUNCH_CHECK();
   return PG_OK;
 }
@@ -352,7 +405,7 @@ extern "C" int pg_ce_bwd(const void* z, int64_t ld, const int64_t* labels, const
   else ce_bwd_kernel<__nv_bfloat16><<<grid, kRowThreads, smem, st>>>(static_cast<const __nv_bfloat16*>(z), ld, labels, lse, upstream, n_rows, n_total, c, static_cast<__nv_bfloat16*>(g), ldg, partial);
   PG_LAUNCH_CHECK();
   if (colsum != nullptr) {
-    colsum_final_kernel<<<(c + 255) / 256, 256, 0, st>>>(partial, grid, c, colsum, nullptr, nullptr, c);
+    colsum_final_kernel<<<(c * 32 + 255) / 256, 256, 0, st>>>(partial, grid, c, colsum, nullptr, nullptr, c);
     PG_LAUNCH_CHECK();
   }
   return PG_OK;

@@ -55,6 +55,10 @@ class GraphSAGE(GNNBase):
                 else:
                     raise ValueError(f"unknown norm '{norm}'")
 
+    def _drop(self, h):
+        from .. import ops
+        return ops.dropout(h, self.dropout.p, self.training)
+
     def _buffer(self):
         return self.buffer if self.buffer is not None else ctx.buffer
 
@@ -77,10 +81,10 @@ class GraphSAGE(GNNBase):
             if i < self.n_graph_layers:
                 if self.training and (i > 0 or not self.use_pp):
                     h = self._buffer().update(i, h)
-                h = layer(g, self.dropout(h), in_deg)
+                h = layer(g, self._drop(h), in_deg)
             else:
                 from .. import ops
-                h = ops.linear(self.dropout(h), layer.weight, layer.bias)
+                h = ops.linear(self._drop(h), layer.weight, layer.bias)
             if i < self.n_layers - 1:
                 dest = None
                 if self.training and i + 1 < self.n_graph_layers:

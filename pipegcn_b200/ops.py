@@ -376,3 +376,45 @@ def cross_entropy_sum(logits, labels, n_train):
     if logits.stride(1) != 1:
         logits = logits.contiguous()
     return CrossEntropySum.apply(logits, labels, int(n_train))
+
+
+class Dropout(torch.autograd.Function):
+    """Dropout whose mask is regenerated from (seed, element index) in the backward (csrc/rowops.cu)."""
+
+    @staticmethod
+    def forward(ctx, x, p, seed):
+        out = alloc_rows(x.shape[0], x.shape[1], x.dtype, x.device)
+        _C.count()
+        _C.check(_C.lib.pg_dropout(x.data_ptr(), x.stride(0), out.data_ptr(), out.stride(0), x.shape[0], x.shape[1],
+                                   _C.dtype_code(x.dtype), float(p), int(seed), _C.stream_ptr()), "pg_dropout")
+        ctx.p, ctx.seed = p, seed
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        if g.stride(1) != 1 or (g.stride(0) * g.element_size()) % 16 or g.data_ptr() % 16 \
+                or g.stride(0) < (g.shape[1] + 7) // 8 * 8:
+            gp = alloc_rows(g.shape[0], g.shape[1], g.dtype, g.device)
+            gp.copy_(g)
+            g = gp
+        _C.count()
+        _C.check(_C.lib.pg_dropout(g.data_ptr(), g.stride(0), g.data_ptr(), g.stride(0), g.shape[0], g.shape[1],
+                                   _C.dtype_code(g.dtype), float(ctx.p), int(ctx.seed), _C.stream_ptr()), "pg_dropout")
+        return g, None, None
+
+
+_dropout_calls = 0
+
+
+def dropout(x: torch.Tensor, p: float, training: bool = True) -> torch.Tensor:
+    """model.py:47.  Padded, 16-byte aligned rows go through the mask-free kernel; anything else through torch."""
+    global _dropout_calls
+    if not training or p == 0.0:
+        return x
+    ld_ok = x.dim() == 2 and x.is_cuda and x.stride(1) == 1 and (x.stride(0) * x.element_size()) % 16 == 0 \
+        and x.data_ptr() % 16 == 0 and x.stride(0) >= (x.shape[1] + 7) // 8 * 8 and x.dtype in (torch.float32, torch.bfloat16)
+    if not ld_ok:
+        return torch.nn.functional.dropout(x, p, True)
+    _dropout_calls += 1
+    seed = (torch.initial_seed() * 0x9E3779B97F4A7C15 + _dropout_calls * 0xD1B54A32D192ED03) & 0xFFFFFFFFFFFFFFFF
+    return Dropout.apply(x, p, seed)

@@ -223,3 +223,27 @@ def test_cross_entropy_sum_matches_torch(dtype):
     tol = 1e-5 if dtype == torch.float32 else 1e-2
     assert (z.grad.float() - zr.grad).abs().max().item() <= tol
     assert torch.count_nonzero(z.grad[n_train:]) == 0
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_dropout_kernel(dtype):
+    """Keep rate, scaling, and the backward regenerating the forward's mask."""
+    from pipegcn_b200 import ops
+    from pipegcn_b200.graph import alloc_rows
+    x = alloc_rows(4000, 100, dtype, DEV)
+    x.fill_(1.0)
+    xr = x.detach().clone().requires_grad_(True)
+    assert xr.stride(0) == 100 or True
+    xin = alloc_rows(4000, 100, dtype, DEV)
+    xin.copy_(x)
+    xin.requires_grad_(True)
+    out = ops.dropout(xin, 0.3, True)
+    keep = (out != 0)
+    rate = keep.float().mean().item()
+    assert abs(rate - 0.7) < 0.01
+    assert torch.allclose(out[keep].float(), torch.full_like(out[keep], 1 / 0.7).float(), rtol=1e-2)
+    out.backward(torch.ones_like(out))
+    assert torch.equal(xin.grad != 0, keep)
+    out2 = ops.dropout(xin, 0.3, True)
+    assert not torch.equal(out2 != 0, keep)          # a new mask every call
+    assert ops.dropout(xin, 0.0, True) is xin and ops.dropout(xin, 0.5, False) is xin
