@@ -31,7 +31,7 @@ class CsrPlan:
             # segments of a few average rows: long enough to amortise the partial write,
             # short enough that the heaviest hub is spread over hundreds of warps
             mean = self.nnz / max(self.n_rows, 1)
-            seg_len = int(os.environ.get("PG_SEG_LEN", 0)) or int(min(4096, max(256, 8 * mean)))
+            seg_len = int(os.environ.get("PG_SEG_LEN", 0)) or int(min(4096, max(512, 16 * mean)))
         self.seg_len = int(seg_len)
         long_mask = deg > self.seg_len
         self.long_row = torch.nonzero(long_mask, as_tuple=True)[0].to(torch.int32)
