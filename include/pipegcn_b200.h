@@ -114,7 +114,7 @@ int pg_row_grid(int32_t n_rows);
 /* out = keep ? x / (1 - p) : 0 with keep a pure function of (seed, element index) -- the backward calls it again on
  * the gradient with the same seed instead of storing a mask (dropout of model.py:47; in place allowed) */
 int pg_dropout(const void* x, int64_t ldx, void* out, int64_t ldo, int32_t n_rows, int32_t d, int dtype, float p,
-               uint64_t seed, void* stream);
+               uint64_t seed, const uint32_t* step_dev, void* stream);
 /* out = relu?(LayerNorm(y) * gamma + beta), mean/rstd [n_rows] kept for the backward; d % (16/elem) == 0 */
 int pg_ln_relu_fwd(const void* y, int64_t ldy, const float* gamma, const float* beta, float eps, int relu,
                    void* out, int64_t ldo, float* mean, float* rstd, int32_t n_rows, int32_t d, int dtype,
@@ -159,8 +159,10 @@ int pg_push_rows_per_cta(void);
 
 /* momentum = m and one_minus = (float)(1 - m) evaluated in double precision by the caller, exactly the two
  * scalars of `t *= m; t += (1 - m) * recv` (feature_buffer.py:190-191) */
+/* the flag value published is `value` (+ *value_dev when value_dev != NULL: an epoch counter that lives on the
+ * device, so that a captured CUDA graph of an epoch can be replayed) */
 int pg_halo_push(const pg_msg* msgs, int32_t n_msgs, int32_t n_ctas, const void* src, int64_t ld_src, int32_t d,
-                 int dtype, float momentum, float one_minus, uint32_t value, void* stream);
+                 int dtype, float momentum, float one_minus, uint32_t value, const uint32_t* value_dev, void* stream);
 
 /*
  * Block the stream until every flags[i] >= value (acquire, system scope).  A bounded spin:
@@ -168,8 +170,8 @@ int pg_halo_push(const pg_msg* msgs, int32_t n_msgs, int32_t n_ctas, const void*
  * and returns, so a dead peer cannot hang the GPU (the reference hangs in gloo wait(),
  * feature_buffer.py:184).
  */
-int pg_halo_wait(const uint32_t* const* flags, int32_t n_flags, uint32_t value, int32_t timeout_ms,
-                 int32_t* status, void* stream);
+int pg_halo_wait(const uint32_t* const* flags, int32_t n_flags, uint32_t value, const uint32_t* value_dev,
+                 int32_t timeout_ms, int32_t* status, void* stream);
 
 /*
  * grad[urow[i], 0:d] += sum_k recv[usrc[k], 0:d]  for k in [uptr[i], uptr[i+1]), in that order

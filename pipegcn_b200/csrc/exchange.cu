@@ -22,7 +22,8 @@ __device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
 template <typename T, int VB>
 __global__ void __launch_bounds__(kPushThreads)
 halo_push_kernel(const pg_msg* __restrict__ msgs, int n_msgs, const T* __restrict__ src, int64_t ld_src, int nvec,
-                 float momentum, float one_minus, uint32_t value) {
+                 float momentum, float one_minus, uint32_t value, const uint32_t* __restrict__ value_dev) {
+  if (value_dev != nullptr) value += *value_dev;     // epoch counter kept on the device (CUDA-graph replay)
   using P = Pack<T, VB>;
   using Raw = typename P::Raw;
   constexpr int V = P::V;
@@ -77,14 +78,17 @@ halo_push_kernel(const pg_msg* __restrict__ msgs, int n_msgs, const T* __restric
   }
 }
 
-__global__ void halo_flag_only_kernel(const pg_msg* __restrict__ msgs, int n_msgs, uint32_t value) {
+__global__ void halo_flag_only_kernel(const pg_msg* __restrict__ msgs, int n_msgs, uint32_t value,
+                                      const uint32_t* __restrict__ value_dev) {
+  if (value_dev != nullptr) value += *value_dev;
   // messages with zero rows still have to publish their flag
   const int m = blockIdx.x * blockDim.x + threadIdx.x;
   if (m < n_msgs && msgs[m].n_rows == 0 && msgs[m].flag != nullptr) st_release_sys(msgs[m].flag, value);
 }
 
 __global__ void halo_wait_kernel(const uint32_t* const* __restrict__ flags, int n_flags, uint32_t value,
-                                 long long timeout_cycles, int* status) {
+                                 const uint32_t* __restrict__ value_dev, long long timeout_cycles, int* status) {
+  if (value_dev != nullptr) value += *value_dev;
   const int i = threadIdx.x;
   if (i >= n_flags) return;
   const uint32_t* f = flags[i];
@@ -144,16 +148,16 @@ static int common_vec(int d, int es, int vb, std::initializer_list<int64_t> lds)
 
 template <typename T>
 static int halo_push_t(const pg_msg* msgs, int n_msgs, int n_ctas, const void* src, int64_t ld_src, int d,
-                       int vb, float momentum, float one_minus, uint32_t value, cudaStream_t st) {
+                       int vb, float momentum, float one_minus, uint32_t value, const uint32_t* value_dev, cudaStream_t st) {
   const int es = sizeof(T);
   const int v = vb / es;
   const int nvec = static_cast<int>(round_up(d, v) / v);
   const T* sp = static_cast<const T*>(src);
   if (n_ctas > 0) {
     switch (vb) {
-      case 16: halo_push_kernel<T, 16><<<n_ctas, kPushThreads, 0, st>>>(msgs, n_msgs, sp, ld_src, nvec, momentum, one_minus, value); break;
-      case 8: halo_push_kernel<T, 8><<<n_ctas, kPushThreads, 0, st>>>(msgs, n_msgs, sp, ld_src, nvec, momentum, one_minus, value); break;
-      case 4: halo_push_kernel<T, 4><<<n_ctas, kPushThreads, 0, st>>>(msgs, n_msgs, sp, ld_src, nvec, momentum, one_minus, value); break;
+      case 16: halo_push_kernel<T, 16><<<n_ctas, kPushThreads, 0, st>>>(msgs, n_msgs, sp, ld_src, nvec, momentum, one_minus, value, value_dev); break;
+      case 8: halo_push_kernel<T, 8><<<n_ctas, kPushThreads, 0, st>>>(msgs, n_msgs, sp, ld_src, nvec, momentum, one_minus, value, value_dev); break;
+      case 4: halo_push_kernel<T, 4><<<n_ctas, kPushThreads, 0, st>>>(msgs, n_msgs, sp, ld_src, nvec, momentum, one_minus, value, value_dev); break;
       default: set_error("pg_halo_push: unsupported vector width %d", vb); return PG_ERR_INVALID;
     }
     PG_LAUNCH_CHECK();
@@ -169,7 +173,8 @@ extern "C" int pg_push_rows_per_cta(void) { return pg::kPushRows; }
 // Buffer.init_buffer with the same padded stride, the host passes d and strides, and the
 // widest vector legal for src is used; destinations must be at least as aligned.
 extern "C" int pg_halo_push(const pg_msg* msgs, int32_t n_msgs, int32_t n_ctas, const void* src, int64_t ld_src,
-                            int32_t d, int dtype, float momentum, float one_minus, uint32_t value, void* stream) {
+                            int32_t d, int dtype, float momentum, float one_minus, uint32_t value, const uint32_t* value_dev,
+                            void* stream) {
   PG_REQUIRE(msgs && n_msgs > 0, "pg_halo_push: no messages");
   PG_REQUIRE(src != nullptr || n_ctas == 0, "pg_halo_push: null source");
   PG_REQUIRE(d > 0 && ld_src >= d, "pg_halo_push: bad sizes");
@@ -179,24 +184,24 @@ extern "C" int pg_halo_push(const pg_msg* msgs, int32_t n_msgs, int32_t n_ctas, 
   int vb = pg::vec_bytes(src, ld_src, es);
   vb = pg::common_vec(d, es, vb, {ld_src});
   int rc;
-  if (dtype == PG_F32) rc = pg::halo_push_t<float>(msgs, n_msgs, n_ctas, src, ld_src, d, vb, momentum, one_minus, value, st);
-  else if (dtype == PG_BF16) rc = pg::halo_push_t<__nv_bfloat16>(msgs, n_msgs, n_ctas, src, ld_src, d, vb, momentum, one_minus, value, st);
+  if (dtype == PG_F32) rc = pg::halo_push_t<float>(msgs, n_msgs, n_ctas, src, ld_src, d, vb, momentum, one_minus, value, value_dev, st);
+  else if (dtype == PG_BF16) rc = pg::halo_push_t<__nv_bfloat16>(msgs, n_msgs, n_ctas, src, ld_src, d, vb, momentum, one_minus, value, value_dev, st);
   else { pg::set_error("pg_halo_push: unknown dtype %d", dtype); return PG_ERR_INVALID; }
   if (rc != PG_OK) return rc;
-  pg::halo_flag_only_kernel<<<(n_msgs + 63) / 64, 64, 0, st>>>(msgs, n_msgs, value);
+  pg::halo_flag_only_kernel<<<(n_msgs + 63) / 64, 64, 0, st>>>(msgs, n_msgs, value, value_dev);
   PG_LAUNCH_CHECK();
   return PG_OK;
 }
 
-extern "C" int pg_halo_wait(const uint32_t* const* flags, int32_t n_flags, uint32_t value, int32_t timeout_ms,
-                            int32_t* status, void* stream) {
+extern "C" int pg_halo_wait(const uint32_t* const* flags, int32_t n_flags, uint32_t value, const uint32_t* value_dev,
+                            int32_t timeout_ms, int32_t* status, void* stream) {
   PG_REQUIRE(n_flags >= 0 && n_flags <= 1024, "pg_halo_wait: bad flag count %d", n_flags);
   if (n_flags == 0) return PG_OK;
   PG_REQUIRE(flags != nullptr, "pg_halo_wait: null flags");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   // clock64 ticks at the SM clock (<= ~2 GHz): a generous upper bound keeps the spin finite
   const long long cycles = static_cast<long long>(timeout_ms) * 2000000ll;
-  pg::halo_wait_kernel<<<1, ((n_flags + 31) / 32) * 32, 0, st>>>(flags, n_flags, value, cycles, status);
+  pg::halo_wait_kernel<<<1, ((n_flags + 31) / 32) * 32, 0, st>>>(flags, n_flags, value, value_dev, cycles, status);
   PG_LAUNCH_CHECK();
   return PG_OK;
 }

@@ -495,13 +495,14 @@ extern "C" int pg_linear(int dtype_in, int dtype_out, const pg_gemm_src* srcs, i
   const int grid = n_tiles < g_sm_count ? n_tiles : g_sm_count;
   const size_t smem = static_cast<size_t>(kStages) * (kABytes + p.n_pad * kRowBytes) + 4 * kSlabBytes /*staging*/ +
                       1024 /*bias*/ + 256 /*barriers*/ + 1024 /*align*/;
-  if (tf32) {
-    PG_CHECK_CUDA(cudaFuncSetAttribute(linear_tcgen05_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-    linear_tcgen05_kernel<true><<<grid, kGemmThreads, smem, st>>>(maps, p);
-  } else {
-    PG_CHECK_CUDA(cudaFuncSetAttribute(linear_tcgen05_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-    linear_tcgen05_kernel<false><<<grid, kGemmThreads, smem, st>>>(maps, p);
+  static bool attr_set = false;       // once: opt in to the full 227 KB of shared memory (not a stream operation)
+  if (!attr_set) {
+    PG_CHECK_CUDA(cudaFuncSetAttribute(linear_tcgen05_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+    PG_CHECK_CUDA(cudaFuncSetAttribute(linear_tcgen05_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+    attr_set = true;
   }
+  if (tf32) linear_tcgen05_kernel<true><<<grid, kGemmThreads, smem, st>>>(maps, p);
+  else linear_tcgen05_kernel<false><<<grid, kGemmThreads, smem, st>>>(maps, p);
   PG_LAUNCH_CHECK();
   return PG_OK;
 }

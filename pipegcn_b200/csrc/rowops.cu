@@ -277,8 +277,9 @@ __device__ __forceinline__ uint32_t mix32(uint32_t x) {       // lowbias32 final
 template <typename T>
 __global__ void __launch_bounds__(256)
 dropout_kernel(const T* __restrict__ x, int64_t ldx, T* __restrict__ out, int64_t ldo, int n_rows, int nvec,
-               uint32_t thresh16, float scale, uint32_t seed_lo, uint32_t seed_hi) {
+               uint32_t thresh16, float scale, uint32_t seed_lo, uint32_t seed_hi, const uint32_t* __restrict__ step_dev) {
   using P = Pack<T, 16>;
+  if (step_dev != nullptr) seed_hi += 0x632be5abU * (*step_dev + 1u);   // device-side epoch counter (graph replay)
   constexpr int V = P::V;
   const int64_t total = static_cast<int64_t>(n_rows) * nvec;
   for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
@@ -307,7 +308,7 @@ static int row_grid(int n_rows) {
 extern "C" int pg_row_grid(int32_t n_rows) { return pg::row_grid(n_rows); }
 
 extern "C" int pg_dropout(const void* x, int64_t ldx, void* out, int64_t ldo, int32_t n_rows, int32_t d, int dtype,
-                          float p, uint64_t seed, void* stream) {
+                          float p, uint64_t seed, const uint32_t* step_dev, void* stream) {
   using namespace pg;
   PG_REQUIRE(x && out && p >= 0.f && p < 1.f, "pg_dropout: bad argument");
   const int es = elem_size(dtype), v = 16 / es;
@@ -321,9 +322,9 @@ extern "C" int pg_dropout(const void* x, int64_t ldx, void* out, int64_t ldo, in
   const float scale = 1.0f / (1.0f - p);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (dtype == PG_F32)
-    dropout_kernel<float><<<blocks, 256, 0, st>>>(static_cast<const float*>(x), ldx, static_cast<float*>(out), ldo, n_rows, nvec, thresh, scale, static_cast<uint32_t>(seed), static_cast<uint32_t>(seed >> 32));
+    dropout_kernel<float><<<blocks, 256, 0, st>>>(static_cast<const float*>(x), ldx, static_cast<float*>(out), ldo, n_rows, nvec, thresh, scale, static_cast<uint32_t>(seed), static_cast<uint32_t>(seed >> 32), step_dev);
   else
-    dropout_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(x), ldx, static_cast<__nv_bfloat16*>(out), ldo, n_rows, nvec, thresh, scale, static_cast<uint32_t>(seed), static_cast<uint32_t>(seed >> 32));
+    dropout_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(x), ldx, static_cast<__nv_bfloat16*>(out), ldo, n_rows, nvec, thresh, scale, static_cast<uint32_t>(seed), static_cast<uint32_t>(seed >> 32), step_dev);
   PG_LAUNCH_CHECK();
   return PG_OK;
 }

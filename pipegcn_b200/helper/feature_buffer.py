@@ -79,6 +79,7 @@ class Buffer(object):
         self._pipeline = False
         self.timeout_ms = 20000
         self.timer = comm_timer
+        self.graph_mode = False      # True while an epoch is captured into / replayed from a CUDA graph
 
     # ------------------------------------------------------------------ set-up
     def init_buffer(self, num_in, num_all, boundary, f_recv_shape, layer_size, use_pp=False, backend='nccl',
@@ -183,6 +184,7 @@ class Buffer(object):
 
         self._counters = torch.zeros(max(1, 4 * L * size * self._nver), dtype=torch.int32, device=dev)
         self._status = torch.zeros(1, dtype=torch.int32, device=dev)
+        self._epoch_dev = torch.zeros(1, dtype=torch.int32, device=dev)    # == self._epoch, readable by kernels
         self._comm_stream = torch.cuda.Stream(device=dev) if dev.type == 'cuda' else None
         self._push_done = {}
         self._keep = []
@@ -269,8 +271,19 @@ class Buffer(object):
 
     # ------------------------------------------------------------------ epoch control
     def next_epoch(self):
+        if self.graph_mode and self._comm_stream is not None:
+            # a captured epoch must re-join the side stream it forked (the pushes of this epoch)
+            torch.cuda.current_stream().wait_stream(self._comm_stream)
         self._epoch += 1
+        self._epoch_dev.add_(1)
         self._keep.clear()
+
+    def _val(self, offset: int):
+        """(value, value_dev) of a flag publish / wait for epoch + offset: a host constant when running eagerly,
+        an offset to the device-side epoch counter when the epoch is captured into a CUDA graph."""
+        if self.graph_mode:
+            return offset & 0xffffffff, self._epoch_dev.data_ptr()
+        return (self._epoch + offset) & 0xffffffff, None
 
     def check_status(self):
         """Raises if a flag wait timed out since the last check (host sync)."""
@@ -280,26 +293,31 @@ class Buffer(object):
                              f"{self.timeout_ms} ms (PG_ERR_TIMEOUT)")
 
     # ------------------------------------------------------------------ kernels
-    def _push(self, ms: Optional[_MsgSet], src: torch.Tensor, d: int, value: int):
+    def _push(self, ms: Optional[_MsgSet], src: torch.Tensor, d: int, offset: int):
+        """`offset`: the flag carries epoch + offset (1 for a message of this epoch)."""
         if ms is None:
             return
+        value, value_dev = self._val(offset)
         _C.count(2)
         _C.check(_C.lib.pg_halo_push(ms.ptr, ms.n_msgs, ms.n_ctas, src.data_ptr(), src.stride(0), d,
                                      _C.dtype_code(src.dtype), self._corr_momentum, 1 - self._corr_momentum,
-                                     value & 0xffffffff,
-                                     _C.stream_ptr()), "pg_halo_push")
+                                     value, value_dev, _C.stream_ptr()), "pg_halo_push")
 
-    def _wait_flags(self, layer: int, direction: int, value: int, name: str):
+    def _wait_flags(self, layer: int, direction: int, offset: int, name: str):
         ptrs = self._wait[(layer, direction)]
         if ptrs is None:
             return
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
+        value, value_dev = self._val(offset)
+        timed = not self.graph_mode                   # timing events cannot be queried inside a captured graph
+        if timed:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
         _C.count()
-        _C.check(_C.lib.pg_halo_wait(ptrs.data_ptr(), ptrs.numel(), value & 0xffffffff, self.timeout_ms,
+        _C.check(_C.lib.pg_halo_wait(ptrs.data_ptr(), ptrs.numel(), value, value_dev, self.timeout_ms,
                                      self._status.data_ptr(), _C.stream_ptr()), "pg_halo_wait")
-        e1.record()
-        self.timer.add_events(name, e0, e1)
+        if timed:
+            e1.record()
+            self.timer.add_events(name, e0, e1)
 
     def _check_feat(self, layer, feat):
         if not self._ready:
@@ -331,8 +349,8 @@ class Buffer(object):
             v = 0
             if not aliased(v):
                 self._push(self._self_msgs[(layer, v)], feat, d, 0)
-            self._push(self._fwd_msgs[(layer, v)], feat, d, t + 1)
-            self._wait_flags(layer, 0, t + 1, f'forward_{layer}')
+            self._push(self._fwd_msgs[(layer, v)], feat, d, 1)
+            self._wait_flags(layer, 0, 1, f'forward_{layer}')
         else:
             v_use, v_send = (t + 1) % 2, t % 2
             v = v_use
@@ -340,16 +358,17 @@ class Buffer(object):
             if not zero_copy:
                 self._push(self._self_msgs[(layer, v_use)], feat, d, 0)
             if t > 0:
-                self._wait_flags(layer, 0, t, f'forward_{layer}')
+                self._wait_flags(layer, 0, 0, f'forward_{layer}')
             ms = self._fwd_msgs[(layer, v_send)]
             if ms is not None:
                 cur = torch.cuda.current_stream()
                 self._comm_stream.wait_stream(cur)
-                feat.record_stream(self._comm_stream)
+                if not self.graph_mode:
+                    feat.record_stream(self._comm_stream)
                 self._keep.append(feat)
                 with torch.cuda.stream(self._comm_stream):
-                    self._push(ms, feat, d, t + 1)
-                    if zero_copy:
+                    self._push(ms, feat, d, 1)
+                    if zero_copy and not self.graph_mode:
                         ev = torch.cuda.Event()
                         ev.record()
                         self._push_done[(layer, v_use)] = ev
@@ -363,22 +382,23 @@ class Buffer(object):
             grad = grad.contiguous()
         if not self._pipeline:
             v = 0
-            self._push(self._bwd_msgs[(layer, v)], grad, d, t + 1)
-            self._wait_flags(layer, 1, t + 1, f'backward_{layer}')
+            self._push(self._bwd_msgs[(layer, v)], grad, d, epoch - self._epoch + 1)
+            self._wait_flags(layer, 1, epoch - self._epoch + 1, f'backward_{layer}')
             self._boundary_add(layer, v, grad)
         else:
             v_use, v_send = (t + 1) % 2, t % 2
             if t > 0:
-                self._wait_flags(layer, 1, t, f'backward_{layer}')
+                self._wait_flags(layer, 1, epoch - self._epoch, f'backward_{layer}')
             self._boundary_add(layer, v_use, grad)
             ms = self._bwd_msgs[(layer, v_send)]
             if ms is not None:
                 cur = torch.cuda.current_stream()
                 self._comm_stream.wait_stream(cur)
-                grad.record_stream(self._comm_stream)
+                if not self.graph_mode:
+                    grad.record_stream(self._comm_stream)
                 self._keep.append(grad)
                 with torch.cuda.stream(self._comm_stream):
-                    self._push(ms, grad, d, t + 1)
+                    self._push(ms, grad, d, epoch - self._epoch + 1)
         return grad[:self._num_in]
 
     def _boundary_add(self, layer, v, grad):

@@ -385,9 +385,10 @@ class Dropout(torch.autograd.Function):
     def forward(ctx, x, p, seed):
         out = alloc_rows(x.shape[0], x.shape[1], x.dtype, x.device)
         _C.count()
+        step = STEP_DEV.data_ptr() if STEP_DEV is not None else None
         _C.check(_C.lib.pg_dropout(x.data_ptr(), x.stride(0), out.data_ptr(), out.stride(0), x.shape[0], x.shape[1],
-                                   _C.dtype_code(x.dtype), float(p), int(seed), _C.stream_ptr()), "pg_dropout")
-        ctx.p, ctx.seed = p, seed
+                                   _C.dtype_code(x.dtype), float(p), int(seed), step, _C.stream_ptr()), "pg_dropout")
+        ctx.p, ctx.seed, ctx.step = p, seed, step
         return out
 
     @staticmethod
@@ -399,11 +400,15 @@ class Dropout(torch.autograd.Function):
             g = gp
         _C.count()
         _C.check(_C.lib.pg_dropout(g.data_ptr(), g.stride(0), g.data_ptr(), g.stride(0), g.shape[0], g.shape[1],
-                                   _C.dtype_code(g.dtype), float(ctx.p), int(ctx.seed), _C.stream_ptr()), "pg_dropout")
+                                   _C.dtype_code(g.dtype), float(ctx.p), int(ctx.seed), ctx.step, _C.stream_ptr()),
+                 "pg_dropout")
         return g, None, None
 
 
 _dropout_calls = 0
+# device int32 step counter mixed into every dropout seed (set while epochs are replayed from a CUDA graph, where
+# the host-side call counter is frozen at capture time)
+STEP_DEV = None
 
 
 def dropout(x: torch.Tensor, p: float, training: bool = True) -> torch.Tensor:

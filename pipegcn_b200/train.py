@@ -87,9 +87,13 @@ class RankEngine:
         for name, p in self.model.named_parameters():
             p.register_hook(reduce_hook(self.reducer, p, name, args.n_train))
         self.loss_fcn = torch.nn.CrossEntropyLoss(reduction='sum')        # train.py:320
-        self.optimizer = torch.optim.Adam(self.model.parameters(), lr=args.lr, weight_decay=args.weight_decay)
+        self.use_graph = bool(getattr(args, 'cuda_graph', False))
+        self.optimizer = torch.optim.Adam(self.model.parameters(), lr=args.lr, weight_decay=args.weight_decay,
+                                          capturable=self.use_graph)
+        self.graphs = None
         self.epoch = 0
         self.last_logits = None
+        self.keep_logits = False
 
     def forward_backward(self, keep_logits=False):
         """train.py:343-355; returns the summed loss (device tensor, no host sync)."""
@@ -101,7 +105,7 @@ class RankEngine:
             loss = ops.cross_entropy_sum(logits, self.labels, self.part_train)      # fused softmax-CE (sum)
         else:
             loss = self.loss_fcn(logits[self.train_sel].float(), self.labels)
-        if keep_logits:
+        if keep_logits or self.keep_logits:
             self.last_logits = logits.detach()
         self.optimizer.zero_grad(set_to_none=True)
         loss.backward()
@@ -109,6 +113,11 @@ class RankEngine:
 
     def set_features(self, feat):
         """New input features for the coming epoch (host or device tensor, [N_in, n_feat])."""
+        if self.graphs is not None:
+            # the captured epochs read layer 0 of a fixed version each: refresh every version (device epoch
+            # parity is not known on the host)
+            self.buffer.load_inner(0, feat.to(self.device, non_blocking=True) if not feat.is_cuda else feat)
+            return
         view = self.buffer.inner_view(0)
         (view if view is not None else self.feat).copy_(feat, non_blocking=True)
 
@@ -121,8 +130,43 @@ class RankEngine:
         self.epoch += 1
 
     def run_epoch(self):
+        if self.graphs is not None:
+            return self.replay()
         loss = self.forward_backward()
         self.finish_epoch()
+        return loss
+
+    # ------------------------------------------------------------------ CUDA graphs
+    def capture(self):
+        """Capture one whole epoch (forward, loss, backward with both halo exchanges, gradient all-reduce, Adam
+        step) into a CUDA graph -- two graphs with --enable-pipeline, one per epoch parity, because the exchange
+        buffers alternate.  Everything that changes from epoch to epoch is read from the device: the epoch counter
+        behind the flag values (`Buffer._epoch_dev`) and the dropout step.  Call after >= 3 eager epochs."""
+        from . import ops
+        assert self.epoch >= 3, "run a few eager epochs first (allocator, lazy handles, steady-state control flow)"
+        assert self.use_graph, "create the engine with args.cuda_graph=True (capturable optimizer)"
+        self.buffer.graph_mode = True
+        self.buffer._push_done.clear()
+        ops.STEP_DEV = self.buffer._epoch_dev
+        torch.cuda.synchronize()
+        graphs = []
+        pool = None
+        for _ in range(2 if self.args.enable_pipeline else 1):
+            g = torch.cuda.CUDAGraph()
+            self.optimizer.zero_grad(set_to_none=True)
+            with torch.cuda.graph(g, pool=pool):
+                loss = self.forward_backward()
+                self.finish_epoch()
+            pool = g.pool()
+            graphs.append((g, loss))
+        torch.cuda.synchronize()
+        self.graphs, self._replays = graphs, 0
+        return self
+
+    def replay(self):
+        g, loss = self.graphs[self._replays % len(self.graphs)]
+        g.replay()
+        self._replays += 1
         return loss
 
 

@@ -138,3 +138,31 @@ def test_engine_matches_reference_golden(name):
             assert abs(float(losses[r].item()) - ep["loss"]) <= 1e-4 * abs(ep["loss"])
             for n, p in eng.model.named_parameters():
                 torch.testing.assert_close(p.grad.cpu(), ep["grads"][n], rtol=2e-3, atol=2e-5)
+
+
+@pytest.mark.parametrize("mode", ["sync", "pipeline_corr"])
+def test_cuda_graph_replay_equals_eager(mode):
+    """Epochs replayed from captured CUDA graphs (device-side epoch counter, one graph per parity) produce what
+    eagerly launched epochs produce: same oracle-forced weights, same logits and gradients."""
+    from oracle.train import initial_state, run_world
+    from pipegcn_b200.train import RankEngine
+    from pipegcn_b200.world import LocalWorld
+    from tests.helpers import make_args, small_world
+    g, _, layouts, setups = small_world("tiny", 1)
+    n_epochs = 7
+    oargs, eargs = make_args(g, 5, n_epochs=n_epochs, **MODES[mode])
+    init = initial_state(oargs)
+    traces = run_world(setups, oargs, init_state=init)
+    eargs.cuda_graph = True
+    eng = RankEngine(layouts[0], eargs, LocalWorld(1, "cuda").view(0), init_state=init, seg_len=32)
+    eng.keep_logits = True
+    for e in range(n_epochs):
+        if e == 3:
+            eng.capture()
+            assert len(eng.graphs) == (2 if eargs.enable_pipeline else 1)
+        eng.model.load_state_dict(traces[0].states[e])
+        loss = eng.run_epoch()
+        torch.testing.assert_close(eng.last_logits.float().cpu(), traces[0].logits[e], rtol=2e-4, atol=2e-4)
+        assert abs(float(loss.item()) - traces[0].losses[e]) <= 1e-4 * abs(traces[0].losses[e])
+        for n, p in eng.model.named_parameters():
+            torch.testing.assert_close(p.grad.cpu(), traces[0].grads[e][n], rtol=2e-3, atol=2e-5)

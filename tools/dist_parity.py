@@ -38,19 +38,23 @@ def main():
     shape = sys.argv[1] if len(sys.argv) > 1 else "tiny"
     n_class = 5 if shape == "tiny" else 16
     g, _, layouts, setups = small_world(shape, size)
-    n_epochs = 4
+    use_graph = os.environ.get("PG_PARITY_GRAPH", "0") == "1"       # epochs >= 3 replayed from CUDA graphs
+    n_epochs = 6 if use_graph else 4
     ok = True
     for mode, kw in MODES.items():
         oargs, eargs = make_args(g, n_class, n_epochs=n_epochs, **kw)
+        eargs.cuda_graph = use_graph
         init = initial_state(oargs)
         traces = run_world(setups, oargs, init_state=init)
         world = DistWorld(device=dev)
         eng = RankEngine(layouts[rank], eargs, world, init_state=init, seg_len=32)
+        eng.keep_logits = True
         worst = 0.0
         for e in range(n_epochs):
+            if use_graph and e == 3:
+                eng.capture()
             eng.model.load_state_dict(traces[0].states[e])      # teacher forcing, see tests/test_engine_gpu.py
-            loss = eng.forward_backward(keep_logits=True)
-            eng.finish_epoch()
+            loss = eng.run_epoch()
             eng.buffer.check_status()
             eng.buffer.timer.clear()
             ref = traces[rank]
@@ -68,7 +72,7 @@ def main():
         if rank == 0:
             good = flag.item() < 2e-3
             ok = ok and good
-            print(f"[dist_parity] {shape} P={size} mode={mode:14s} worst relative error {flag.item():.3e} "
+            print(f"[dist_parity] {shape} P={size} graph={int(use_graph)} mode={mode:14s} worst relative error {flag.item():.3e} "
                   f"{'OK' if good else 'FAIL'}", flush=True)
         del eng
         dist.barrier()
