@@ -187,6 +187,7 @@ class Buffer(object):
         self._epoch_dev = torch.zeros(1, dtype=torch.int32, device=dev)    # == self._epoch, readable by kernels
         self._comm_stream = torch.cuda.Stream(device=dev) if dev.type == 'cuda' else None
         self._push_done = {}
+        self._comm_forked = False
         self._keep = []
 
         w.publish('pipegcn.buffer', {
@@ -271,9 +272,11 @@ class Buffer(object):
 
     # ------------------------------------------------------------------ epoch control
     def next_epoch(self):
-        if self.graph_mode and self._comm_stream is not None:
-            # a captured epoch must re-join the side stream it forked (the pushes of this epoch)
+        if self.graph_mode and self._comm_forked:
+            # a captured epoch must re-join the side stream it forked (the pushes of this epoch); a stream that
+            # was not forked into the capture must not be waited on (cudaErrorStreamCaptureIsolation)
             torch.cuda.current_stream().wait_stream(self._comm_stream)
+        self._comm_forked = False
         self._epoch += 1
         self._epoch_dev.add_(1)
         self._keep.clear()
@@ -363,6 +366,7 @@ class Buffer(object):
             if ms is not None:
                 cur = torch.cuda.current_stream()
                 self._comm_stream.wait_stream(cur)
+                self._comm_forked = True
                 if not self.graph_mode:
                     feat.record_stream(self._comm_stream)
                 self._keep.append(feat)
@@ -394,6 +398,7 @@ class Buffer(object):
             if ms is not None:
                 cur = torch.cuda.current_stream()
                 self._comm_stream.wait_stream(cur)
+                self._comm_forked = True
                 if not self.graph_mode:
                     grad.record_stream(self._comm_stream)
                 self._keep.append(grad)
