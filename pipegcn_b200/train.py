@@ -158,15 +158,16 @@ class RankEngine:
                 loss = self.forward_backward()
                 self.finish_epoch()
             pool = g.pool()
-            graphs.append((g, loss))
+            graphs.append((g, loss, self.last_logits))
         torch.cuda.synchronize()
         self.graphs, self._replays = graphs, 0
         return self
 
     def replay(self):
-        g, loss = self.graphs[self._replays % len(self.graphs)]
+        g, loss, logits = self.graphs[self._replays % len(self.graphs)]
         g.replay()
         self._replays += 1
+        self.last_logits = logits
         return loss
 
 
