@@ -336,9 +336,13 @@ def main():
             "roofline": roofline, "e2e": e2e, "cpu_baseline": cb, "gpu_launches": launches, "clocks": clocks,
         }
         print(json.dumps(line), flush=True)
+    sys.stdout.flush()
+    engine.graphs = None            # drop captured graphs (they hold NCCL kernels) before the communicator goes away
+    torch.cuda.synchronize()
     if world_size > 1:
         dist.barrier()
-        dist.destroy_process_group()
+        torch.cuda.synchronize()
+    os._exit(0)                     # skip NCCL communicator teardown (can block behind captured graphs)
 
 
 if __name__ == "__main__":

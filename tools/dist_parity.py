@@ -41,7 +41,10 @@ def main():
     use_graph = os.environ.get("PG_PARITY_GRAPH", "0") == "1"       # epochs >= 3 replayed from CUDA graphs
     n_epochs = 6 if use_graph else 4
     ok = True
+    only = os.environ.get("PG_PARITY_MODES")
     for mode, kw in MODES.items():
+        if only and mode not in only.split(","):
+            continue
         oargs, eargs = make_args(g, n_class, n_epochs=n_epochs, **kw)
         eargs.cuda_graph = use_graph
         init = initial_state(oargs)
@@ -65,6 +68,8 @@ def main():
                 gd = (p.grad.float().cpu() - ref.grads[e][n]).abs().max().item()
                 worst = max(worst, gd / max(ref.grads[e][n].abs().max().item(), 1e-6))
             worst = max(worst, dl)
+            if os.environ.get("PG_PARITY_VERBOSE") and rank == 0:
+                print(f"[dist_parity]   mode={mode} epoch {e} graph={int(eng.graphs is not None)} logits err {d:.3e} loss rel {dl:.3e} worst {worst:.3e}", flush=True)
         eng.buffer.synchronize()
         torch.cuda.synchronize()
         flag = torch.tensor([worst], device=dev)
@@ -74,12 +79,15 @@ def main():
             ok = ok and good
             print(f"[dist_parity] {shape} P={size} graph={int(use_graph)} mode={mode:14s} worst relative error {flag.item():.3e} "
                   f"{'OK' if good else 'FAIL'}", flush=True)
+        eng.graphs = None
         del eng
+        torch.cuda.synchronize()
         dist.barrier()
-    dist.destroy_process_group()
     if rank == 0:
         print("[dist_parity] " + ("ALL OK" if ok else "FAILED"), flush=True)
-        sys.exit(0 if ok else 1)
+    sys.stdout.flush()
+    torch.cuda.synchronize()
+    os._exit(0 if (ok or rank != 0) else 1)
 
 
 if __name__ == "__main__":
