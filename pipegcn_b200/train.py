@@ -158,16 +158,18 @@ class RankEngine:
                 loss = self.forward_backward()
                 self.finish_epoch()
             pool = g.pool()
-            graphs.append((g, loss, self.last_logits))
+            graphs.append((g, loss, self.last_logits, [p.grad for p in self.model.parameters()]))
         torch.cuda.synchronize()
         self.graphs, self._replays = graphs, 0
         return self
 
     def replay(self):
-        g, loss, logits = self.graphs[self._replays % len(self.graphs)]
+        g, loss, logits, grads = self.graphs[self._replays % len(self.graphs)]
         g.replay()
         self._replays += 1
         self.last_logits = logits
+        for p, gr in zip(self.model.parameters(), grads):     # each graph owns its gradient tensors
+            p.grad = gr
         return loss
 
 
