@@ -69,6 +69,7 @@ class GlooFabric:
 
     def send(self, tensor, src, dst, tag):
         t = tensor.detach().clone().contiguous()
+        self._pending = [(r, b) for r, b in self._pending if not r.is_completed()]
         self._pending.append((self.dist.isend(t, dst=dst, tag=tag), t))
 
     def recv(self, src, dst, tag, shape=None, dtype=torch.float32, timeout=None):
