@@ -123,8 +123,8 @@ class OracleGraphSAGE(nn.Module):
             if i < self.n_layers - self.n_linear:
                 if self.training and (i > 0 or not self.use_pp):
                     h = buffer.update(i, h)
-                    if tr is not None:
-                        tr["f_buf"] = h.detach().clone()
+                if tr is not None:
+                    tr["f_buf"] = h.detach().clone()           # what the layer consumes (before dropout)
                 h = self.dropout(h)
                 h = self.layers[i](g, h, in_deg, trace=tr)
             else:

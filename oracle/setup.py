@@ -156,3 +156,18 @@ def setup_world(parts: List[DglPartition]) -> List[RankSetup]:
         out.append(RankSetup(rank, size, num_in, num_all, u, v, nd["in_degree"], boundary,
                              get_recv_shape(p, rank, size), nd))
     return out
+
+
+def precompute(setups: List[RankSetup]) -> List[torch.Tensor]:
+    """`--use-pp` (train.py:169-189 with data_transfer / merge_feature, utils.py:191-223): one exchange of the raw
+    boundary features, neighbour mean over the `_U` graph, feat <- cat(feat, mean) [N_in, 2 * n_feat]."""
+    size = len(setups)
+    out = []
+    for r, s in enumerate(setups):
+        feat = s.node_dict["feat"]
+        recv = [setups[j].node_dict["feat"][setups[j].boundary[r]] for j in range(size) if j != r]   # ascending peers
+        merged = torch.cat([feat] + recv)                                   # merge_feature, utils.py:216-223
+        summed = torch.zeros(s.num_in, feat.shape[1]).index_add_(0, s.v, merged[s.u])
+        mean = summed / s.in_deg[0:s.num_in].unsqueeze(1)                   # train.py:186
+        out.append(torch.cat([feat, mean[0:s.num_in]], dim=1))              # train.py:187
+    return out

@@ -143,8 +143,12 @@ def run_world(setups: List[RankSetup], args: OracleArgs, init_state=None, keep_t
     fabric = ThreadFabric(size)
     out: List[Optional[RankTrace]] = [None] * size
     err: List[Optional[BaseException]] = [None] * size
+    feats = [None] * size
+    if args.use_pp:                                                        # train.py:287-288
+        from .setup import precompute
+        feats = precompute(setups)
     if size == 1:
-        return [run_rank(setups[0], args, fabric, init_state, keep_trace, forced_states=forced_states)]
+        return [run_rank(setups[0], args, fabric, init_state, keep_trace, feat=feats[0], forced_states=forced_states)]
     torch.set_num_threads(max(1, torch.get_num_threads() // size))
 
     # every rank seeds the global RNG identically before building its model (train.py:298); with threads the
@@ -158,7 +162,8 @@ def run_world(setups: List[RankSetup], args: OracleArgs, init_state=None, keep_t
 
     def work(r):
         try:
-            out[r] = run_rank(setups[r], args, fabric, init_state, keep_trace, forced_states=forced_states)
+            out[r] = run_rank(setups[r], args, fabric, init_state, keep_trace, feat=feats[r],
+                              forced_states=forced_states)
         except BaseException as e:   # noqa: BLE001
             err[r] = e
             try:

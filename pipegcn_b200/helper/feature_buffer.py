@@ -84,7 +84,7 @@ class Buffer(object):
     # ------------------------------------------------------------------ set-up
     def init_buffer(self, num_in, num_all, boundary, f_recv_shape, layer_size, use_pp=False, backend='nccl',
                     pipeline=False, corr_feat=False, corr_grad=False, corr_momentum=0,
-                    dtype=torch.float32, world=None):
+                    dtype=torch.float32, world=None, key='pipegcn.buffer'):
         if backend not in ('nccl', 'nvlink'):
             # the reference implements gloo only and raises for the rest (feature_buffer.py:204-205);
             # this engine implements the NVLink path only
@@ -190,7 +190,8 @@ class Buffer(object):
         self._comm_forked = False
         self._keep = []
 
-        w.publish('pipegcn.buffer', {
+        self._key = key
+        w.publish(key, {
             'heap': w.heap_token(self._heap), 'f_off': dict(self._f_off), 'b_off': dict(self._b_off),
             'flag_off': self._flag_off, 'pl': list(self._pl), 'boff': list(self._boff), 'ld': list(self._ld),
             'n_layers': L, 'nver': self._nver, 'es': self._es,
@@ -201,7 +202,7 @@ class Buffer(object):
         """Map the peers' heaps and build the message descriptors (needs every rank's table)."""
         w = self._world
         rank, size, dev = w.rank, w.size, w.device
-        tables = w.collect('pipegcn.buffer')
+        tables = w.collect(self._key)
         base = {j: w.map_peer(tables[j]['heap']) for j in range(size)}
         L, es = self._n_layers, self._es
         for j in self._peers:

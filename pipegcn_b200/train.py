@@ -67,11 +67,15 @@ class RankEngine:
                                 backend=args.backend, pipeline=args.enable_pipeline, corr_feat=args.feat_corr,
                                 corr_grad=args.grad_corr, corr_momentum=args.corr_momentum,
                                 dtype=self.dtype, world=world)
-        if args.use_pp:
-            raise NotImplementedError("--use-pp precompute is scheduled after the core path (SURVEY.md §8f-2)")
         self.feat = layout.feat.to(dev).to(self.dtype)
-        # the static input features live in the exchange buffer of layer 0 (all versions): update(0, .) copies nothing
-        self.buffer.load_inner(0, self.feat)
+        self._pp = None
+        if args.use_pp:
+            self.pp_begin(layout)
+            if not getattr(world, 'is_local', False) or world.size == 1:
+                self.pp_end()
+        else:
+            # the static input features live in the exchange buffer of layer 0 (all versions): update(0, .) copies nothing
+            self.buffer.load_inner(0, self.feat)
         tm = layout.train_mask.to(dev)
         self.part_train = int(tm.sum().item())
         prefix = bool(tm[:self.part_train].all().item()) if self.part_train else True
@@ -94,6 +98,48 @@ class RankEngine:
         self.epoch = 0
         self.last_logits = None
         self.keep_logits = False
+
+    # ------------------------------------------------------------------ --use-pp (train.py:169-189)
+    def pp_begin(self, layout):
+        """One-shot exchange of the raw boundary features through the push kernel (first half of `precompute`)."""
+        from .graph import alloc_rows
+        pp = Buffer(self.world)
+        pp.timer = CommTimer()
+        pp.init_buffer(layout.num_in, layout.num_all, layout.boundary, layout.recv_shape, [self.args.n_feat],
+                       backend=self.args.backend, pipeline=False, dtype=self.dtype, world=self.world,
+                       key='pipegcn.buffer.pp')
+        self._pp = pp
+        self._pp_started = False
+
+    def _pp_push(self):
+        pp = self._pp
+        pp._connect()
+        d = self.args.n_feat
+        feat = self.feat if self.feat.stride(1) == 1 else self.feat.contiguous()
+        pp._push(pp._self_msgs[(0, 0)], feat, d, 0)
+        pp._push(pp._fwd_msgs[(0, 0)], feat, d, 1)
+        self._pp_started = True
+
+    def pp_end(self):
+        """Wait for the peers' rows, neighbour mean, feat <- cat(feat, mean) (second half of `precompute`).  With
+        several LocalWorld ranks in one process every rank must have pushed before any rank waits
+        (`LocalTrainer` calls `_pp_push` on all engines first)."""
+        from . import ops
+        from .graph import alloc_rows
+        pp = self._pp
+        if not self._pp_started:
+            self._pp_push()
+        pp._wait_flags(0, 0, 1, 'forward_0')
+        d = self.args.n_feat
+        merged = pp._f_buf[(0, 0)][:, :d]
+        mean = ops.aggregate(self.graph.fwd, merged, row_div=self.graph.in_deg_f)
+        both = alloc_rows(self.graph.num_in, 2 * d, self.dtype, self.device)
+        both[:, :d].copy_(self.feat)
+        both[:, d:].copy_(mean)
+        self.feat = both
+        torch.cuda.synchronize()
+        pp.check_status()
+        self._pp = None
 
     def forward_backward(self, keep_logits=False):
         """train.py:343-355; returns the summed loss (device tensor, no host sync)."""
@@ -183,6 +229,13 @@ class LocalTrainer:
         self.world = local_world
         self.engines = [RankEngine(l, args, local_world.view(r), init_state=init_state, seg_len=seg_len)
                         for r, l in enumerate(layouts)]
+        if args.use_pp and len(layouts) > 1:          # all ranks push before any rank waits (one host thread)
+            for e, s in zip(self.engines, self.streams):
+                with torch.cuda.stream(s):
+                    e._pp_push()
+            for e, s in zip(self.engines, self.streams):
+                with torch.cuda.stream(s):
+                    e.pp_end()
         for e in self.engines:
             e.buffer.timeout_ms = 5000
 

@@ -25,6 +25,7 @@ CONFIGS = {
     "sync_corr_p2": dict(n_parts=2, feat_corr=True, grad_corr=True, corr_momentum=0.9),
     "pipeline_p2": dict(n_parts=2, enable_pipeline=True),
     "pipeline_corr_p3": dict(n_parts=3, enable_pipeline=True, feat_corr=True, grad_corr=True, corr_momentum=0.95),
+    "pipeline_pp_p2": dict(n_parts=2, enable_pipeline=True, use_pp=True),
 }
 N_EPOCHS, N_LAYERS, N_HIDDEN, N_CLASS, SEED = 3, 3, 16, 5, 0
 
@@ -58,7 +59,7 @@ def worker(rank, size, name, cfg, port, q):
     node_dict = dict(p.node_dict)
     node_dict[dgl.NID] = node_dict.pop(dglpart.NID)
     gpb = p.gpb
-    args = argparse.Namespace(model="graphsage", use_pp=False, norm="layer", dropout=0.0, n_linear=0,
+    args = argparse.Namespace(model="graphsage", use_pp=cfg.get("use_pp", False), norm="layer", dropout=0.0, n_linear=0,
                               n_train=int(g.train_mask.sum()), n_feat=g.n_feat, n_hidden=N_HIDDEN, n_class=N_CLASS,
                               n_layers=N_LAYERS, backend="gloo", enable_pipeline=cfg.get("enable_pipeline", False),
                               feat_corr=cfg.get("feat_corr", False), grad_corr=cfg.get("grad_corr", False),
@@ -78,6 +79,8 @@ def worker(rank, size, name, cfg, port, q):
     ctx.buffer.init_buffer(num_in, graph.num_nodes("_U"), boundary, recv_shape, layer_size[:args.n_layers - args.n_linear],
                            use_pp=args.use_pp, backend=args.backend, pipeline=args.enable_pipeline,
                            corr_feat=args.feat_corr, corr_grad=args.grad_corr, corr_momentum=args.corr_momentum)
+    if args.use_pp:                                        # train.py:287-288, the reference's own precompute
+        node_dict["feat"] = T.precompute(graph, node_dict, boundary, recv_shape, args)
     labels = node_dict["label"][node_dict["train_mask"]]
     train_mask = node_dict["train_mask"]
     torch.manual_seed(args.seed)
@@ -101,7 +104,8 @@ def worker(rank, size, name, cfg, port, q):
 
     def hook(i):
         def fn(mod, inp, outp):
-            rec[i] = dict(f_buf=inp[1].detach().clone(), layer_out=outp.detach().clone())
+            src = inp[1] if len(inp) > 1 else inp[0]
+            rec[i] = dict(f_buf=src.detach().clone(), layer_out=outp.detach().clone())
         return fn
     for i, layer in enumerate(model.layers):
         layer.register_forward_hook(hook(i))

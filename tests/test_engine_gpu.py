@@ -101,7 +101,8 @@ def test_exposed_comm_timer_sections():
         trainer.engines[0].buffer.timer.add_events("forward_0", None, None)   # duplicate name, as the reference
 
 
-@pytest.mark.parametrize("name", ["ref_sync_p2.pt", "ref_sync_corr_p2.pt", "ref_pipeline_p2.pt", "ref_pipeline_corr_p3.pt"])
+@pytest.mark.parametrize("name", ["ref_sync_p2.pt", "ref_sync_corr_p2.pt", "ref_pipeline_p2.pt", "ref_pipeline_corr_p3.pt",
+                                  "ref_pipeline_pp_p2.pt"])
 def test_engine_matches_reference_golden(name):
     """The CUDA engine against the committed outputs of the unmodified reference (tests/golden): per-layer inputs
     and outputs, logits, loss, reduced gradients; fp32, teacher-forced weights.  Tolerances: exchange/aggregate
@@ -117,13 +118,14 @@ def test_engine_matches_reference_golden(name):
     layouts = build_layouts(g, part, P)
     _, eargs = make_args(g, c["n_class"], n_epochs=c["n_epochs"], n_layers=c["n_layers"], n_hidden=c["n_hidden"],
                          enable_pipeline=c.get("enable_pipeline", False), feat_corr=c.get("feat_corr", False),
-                         grad_corr=c.get("grad_corr", False), corr_momentum=c.get("corr_momentum", 0.95))
+                         grad_corr=c.get("grad_corr", False), corr_momentum=c.get("corr_momentum", 0.95),
+                         use_pp=c.get("use_pp", False))
     trainer = LocalTrainer(layouts, eargs, LocalWorld(P, "cuda"), init_state=fx["ranks"][0]["init_state"], seg_len=32)
     caps = [dict() for _ in range(P)]
     for r, eng in enumerate(trainer.engines):
         for i, layer in enumerate(eng.model.layers):
             def hook(mod, inp, out, r=r, i=i):
-                caps[r][i] = (inp[1].detach(), out.detach())
+                caps[r][i] = ((inp[1] if len(inp) > 1 else inp[0]).detach(), out.detach())
             layer.register_forward_hook(hook)
     for e in range(c["n_epochs"]):
         for eng in trainer.engines:

@@ -28,7 +28,8 @@ def oracle_args(fx, g):
     return OracleArgs(n_layers=c["n_layers"], n_hidden=c["n_hidden"], n_feat=g.n_feat, n_class=c["n_class"],
                       n_train=int(g.train_mask.sum()), dropout=0.0, lr=c["lr"], n_epochs=c["n_epochs"], seed=c["seed"],
                       enable_pipeline=c.get("enable_pipeline", False), feat_corr=c.get("feat_corr", False),
-                      grad_corr=c.get("grad_corr", False), corr_momentum=c.get("corr_momentum", 0.95))
+                      grad_corr=c.get("grad_corr", False), corr_momentum=c.get("corr_momentum", 0.95),
+                      use_pp=c.get("use_pp", False))
 
 
 def test_fixtures_exist():
@@ -53,7 +54,8 @@ def test_layouts_equal_reference_setup(name):
         for a, b, c in zip(ref["boundary"], S.boundary, L.boundary):
             assert (a is None and b is None and c is None) or (torch.equal(a, b) and torch.equal(a, c))
         assert torch.equal(ref["in_deg"][: S.num_in], S.in_deg) and torch.equal(S.in_deg, L.in_deg)
-        assert torch.equal(ref["feat"][: S.num_in], S.node_dict["feat"]) and torch.equal(S.node_dict["feat"], L.feat)
+        n_feat = S.node_dict["feat"].shape[1]            # with --use-pp the reference's feat is cat(feat, mean)
+        assert torch.equal(ref["feat"][: S.num_in, :n_feat], S.node_dict["feat"]) and torch.equal(S.node_dict["feat"], L.feat)
         assert torch.equal(ref["label"], L.label) and torch.equal(ref["train_mask"], L.train_mask)
 
 
