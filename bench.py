@@ -299,8 +299,12 @@ def main():
     agg_bytes = sum(nb for _, _, nb in prof)
     n_agg = len(prof)
     achieved = (agg_bytes / 1e9) / (agg_ms / 1e3) if agg_ms > 0 else 0.0
+    traffic = None
+    tf = ROOT / "profiles" / "agg_traffic.json"
+    if tf.exists():       # per-launch DRAM bytes of the aggregate kernel from the committed `ncu --set full` capture
+        traffic = json.loads(tf.read_text()).get(f"{args.workload}:{world_size}")
     roofline = {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                "traffic": None, "kernel": "pg::agg_kernel (+fix-up), forward and backward aggregate",
+                "traffic": traffic, "kernel": "pg::agg_kernel (+fix-up), forward and backward aggregate",
                 "launches": n_agg, "avg_launch_ms": agg_ms / max(n_agg, 1),
                 "algorithmic_bytes_per_launch": agg_bytes / max(n_agg, 1),
                 "share_of_step": agg_ms / ms_eager_total if ms_eager_total else None, "peak_source": peak_src,
