@@ -66,7 +66,8 @@ typedef struct pg_csr {
  * Neighbour aggregate:
  *   out[r, 0:d] = ( sum_{e in row r} x[indices[e], 0:d] ) / row_div[r]  ( + out[r, 0:d] if r < acc_rows )
  * x and out have element type `dtype`, sums are fp32.  ldx/ldo are row strides in elements.
- * row_div (fp32, [n_rows]) may be NULL (no division).  scratch: fp32 [n_seg * d_pad] where
+ * row_div (fp32, [n_rows]) may be NULL (no division); the division is one IEEE reciprocal per row and a multiply per
+ * element (within 1 ulp of `/`).  scratch: fp32 [n_seg * d_pad] where
  * d_pad = d rounded up to 8; may be NULL when n_seg == 0.
  * Replaces graph['_E'].update_all(fn.copy_src, fn.sum) and `/ degs` at
  * /root/reference/module/layer.py:47-50, and their autograd.

@@ -97,7 +97,10 @@ agg_kernel(pg_csr g, const T* __restrict__ x, uint32_t ldx_bytes, T* __restrict_
         for (int i = 0; i < V; ++i) sp[o + i] = (i & 1) ? acc[j][i / 2].y : acc[j][i / 2].x;
       }
     } else {
-      const float dv = row_div ? __ldg(row_div + row) : 1.f;
+      // `/ degs` (layer.py:50) as one IEEE reciprocal per row and a multiply per element (<= 1 ulp from the
+      // division): the per-element IEEE division took its slow path on every exact zero (dropout) and was
+      // 79 % of the kernel's instructions in the first ncu capture
+      const float inv = row_div ? 1.f / __ldg(row_div + row) : 1.f;
       T* op = out + static_cast<int64_t>(row) * ldo;
 #pragma unroll
       for (int j = 0; j < VPL; ++j) {
@@ -107,7 +110,7 @@ agg_kernel(pg_csr g, const T* __restrict__ x, uint32_t ldx_bytes, T* __restrict_
 #pragma unroll
         for (int i = 0; i < V; ++i) {
           const float a = (i & 1) ? acc[j][i / 2].y : acc[j][i / 2].x;
-          r[i] = row_div ? a / dv : a;
+          r[i] = a * inv;
         }
         if (row < acc_rows) {
           float ov[V];
@@ -131,7 +134,7 @@ agg_fixup_kernel(pg_csr g, T* __restrict__ out, int64_t ldo, int nvec, const flo
   const int li = blockIdx.x;
   const int row = g.long_row[li];
   const int s0 = g.long_seg_ptr[li], s1 = g.long_seg_ptr[li + 1];
-  const float dv = row_div ? row_div[row] : 1.f;
+  const float inv = row_div ? 1.f / row_div[row] : 1.f;
   T* op = out + static_cast<int64_t>(row) * ldo;
   for (int vi = threadIdx.x; vi < nvec; vi += blockDim.x) {
     float r[V];
@@ -143,7 +146,7 @@ agg_fixup_kernel(pg_csr g, T* __restrict__ out, int64_t ldo, int nvec, const flo
       for (int i = 0; i < V; ++i) r[i] += sp[i];
     }
 #pragma unroll
-    for (int i = 0; i < V; ++i) r[i] = row_div ? r[i] / dv : r[i];
+    for (int i = 0; i < V; ++i) r[i] *= inv;
     if (row < acc_rows) {
       float o[V];
       P::unpack(*reinterpret_cast<const typename P::Raw*>(op + static_cast<int64_t>(vi) * V), o);
@@ -240,9 +243,9 @@ row_div_kernel(const T* __restrict__ x, int64_t ldx, T* __restrict__ out, int64_
     const int r = static_cast<int>(i / nvec), vi = static_cast<int>(i % nvec);
     float f[V];
     P::unpack(ld_vec<VB>(x + static_cast<int64_t>(r) * ldx + static_cast<int64_t>(vi) * V), f);
-    const float dv = __ldg(row_div + r);
+    const float inv = 1.f / __ldg(row_div + r);
 #pragma unroll
-    for (int k = 0; k < V; ++k) f[k] = f[k] / dv;
+    for (int k = 0; k < V; ++k) f[k] *= inv;
     st_vec<VB>(out + static_cast<int64_t>(r) * ldo + static_cast<int64_t>(vi) * V, P::pack(f));
   }
 }
