@@ -123,8 +123,8 @@ def cpu_reference_run(w, args, steps, warmup):
     scale = max(1, args.cpu_scale)
     spec["n_nodes"] //= scale
     spec["n_edges"] //= scale
-    cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
+    from oracle.cbuild import set_threads
+    n_cpu = os.cpu_count() or 1
     g = make_graph(spec, device="cpu")
     part = torch.zeros(g.n_nodes, dtype=torch.int64)
     parts = dglpart.partition_graph(g.n_nodes, g.src, g.dst, part, 1, g.feat, g.label, g.train_mask)
@@ -133,12 +133,25 @@ def cpu_reference_run(w, args, steps, warmup):
     oargs = OracleArgs(n_layers=w["n_layers"], n_hidden=w["n_hidden"], n_feat=g.n_feat, n_class=spec["n_class"],
                        n_train=int(g.train_mask.sum()), dropout=args.dropout, n_epochs=n_ep,
                        enable_pipeline=w["enable_pipeline"], feat_corr=w["feat_corr"], grad_corr=w["grad_corr"])
+    # all the host threads it can USE: on many-core hosts the fastest setting is below the core count, so one
+    # epoch is timed at a few thread counts first and the fastest is kept
+    cand = sorted({t for t in (8, 16, 32, 64, n_cpu) if t <= n_cpu})
+    probe = OracleArgs(**{**oargs.__dict__, "n_epochs": 2})
+    best = None
+    for t in cand:
+        set_threads(t)
+        w1 = run_rank(setups[0], probe, ThreadFabric(1), keep_trace=False).wall[-1]
+        if best is None or w1 < best[0]:
+            best = (w1, t)
+    cores = best[1]
+    set_threads(cores)
     tr = run_rank(setups[0], oargs, ThreadFabric(1), keep_trace=False)
     per_epoch = sum(tr.wall[warmup:]) / max(len(tr.wall[warmup:]), 1)
     eps_sample = 1.0 / max(per_epoch, 1e-9)
     return {
         "value": eps_sample / scale, "unit": "epochs/s", "cores": cores, "kind": "port",
-        "sample": (f"oracle (CPU port of the reference, torch {torch.__version__}, {cores} threads) on a 1/{scale}-scale "
+        "sample": (f"oracle (CPU port of the reference, torch {torch.__version__}, {cores} of {n_cpu} host threads -- the "
+                   f"fastest of {cand}) on a 1/{scale}-scale "
                    f"graph of the same shape ({g.n_nodes} nodes, {g.n_edges} edges, 1 partition), {steps} epochs after "
                    f"{warmup} warm-up: {eps_sample:.3f} epochs/s on the sample; value = that / {scale} "
                    f"(linear-in-edges equivalent for the full graph)"),

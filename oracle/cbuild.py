@@ -27,4 +27,13 @@ def lib():
         vp, i64 = ctypes.c_void_p, ctypes.c_int64
         _lib.oracle_spmm_sum_f32.argtypes = [vp, vp, vp, vp, i64, i64]
         _lib.oracle_spmm_sum_f32.restype = None
+        _lib.oracle_set_threads.argtypes = [ctypes.c_int]
+        _lib.oracle_get_max_threads.restype = ctypes.c_int
     return _lib
+
+
+def set_threads(n: int):
+    """Threads of the C SpMM (OpenMP) and of torch's CPU kernels."""
+    import torch
+    lib().oracle_set_threads(int(n))
+    torch.set_num_threads(int(n))

@@ -8,8 +8,13 @@
  * over a 0/1 adjacency is exactly this row-wise sum.  fp32 accumulation in edge order,
  * rows distributed over OpenMP threads (DGL's CPU SpMM is OpenMP-parallel over rows too).
  */
+#include <omp.h>
 #include <stdint.h>
 #include <string.h>
+
+/* torchrun exports OMP_NUM_THREADS=1 to its workers: the CPU baseline sets its thread count explicitly */
+void oracle_set_threads(int n) { if (n > 0) omp_set_num_threads(n); }
+int oracle_get_max_threads(void) { return omp_get_max_threads(); }
 
 void oracle_spmm_sum_f32(const int64_t* indptr, const int64_t* indices, const float* x, float* out,
                          int64_t n_rows, int64_t d) {
