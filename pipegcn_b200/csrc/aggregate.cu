@@ -99,7 +99,7 @@ agg_kernel(pg_csr g, const T* __restrict__ x, uint32_t ldx_bytes, T* __restrict_
     } else {
       // `/ degs` (layer.py:50) as one IEEE reciprocal per row and a multiply per element (<= 1 ulp from the
       // division): the per-element IEEE division took its slow path on every exact zero (dropout) and was
-      // 79 % of the kernel's instructions in the first ncu capture
+      // a third of the kernel's instructions in the ncu source view
       const float inv = row_div ? 1.f / __ldg(row_div + row) : 1.f;
       T* op = out + static_cast<int64_t>(row) * ldo;
 #pragma unroll
