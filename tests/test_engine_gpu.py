@@ -168,3 +168,39 @@ def test_cuda_graph_replay_equals_eager(mode):
         assert abs(float(loss.item()) - traces[0].losses[e]) <= 1e-4 * abs(traces[0].losses[e])
         for n, p in eng.model.named_parameters():
             torch.testing.assert_close(p.grad.cpu(), traces[0].grads[e][n], rtol=2e-3, atol=2e-5)
+
+
+@pytest.mark.parametrize("mode", ["sync", "pipeline_corr"])
+def test_engine_with_empty_messages(mode):
+    """A chain graph cut into three runs: ranks 0 and 2 share no edge, so their messages have zero rows (the flag
+    is still published) and rank 1 borrows exactly one row from each neighbour."""
+    from oracle import dglpart
+    from oracle import setup as osetup
+    from oracle.train import initial_state, run_world
+    from pipegcn_b200.partition import build_layouts
+    from pipegcn_b200.synthetic import GlobalGraph
+    from pipegcn_b200.train import LocalTrainer
+    from pipegcn_b200.world import LocalWorld
+    from tests.helpers import make_args
+    n, P = 90, 3
+    a = torch.arange(n - 1)
+    loops = torch.arange(n)
+    src, dst = torch.cat([a, a + 1, loops]), torch.cat([a + 1, a, loops])
+    gen = torch.Generator().manual_seed(0)
+    g = GlobalGraph(n, src, dst, torch.randn(n, 12, generator=gen), torch.randint(0, 4, (n,), generator=gen),
+                    torch.rand(n, generator=gen) < 0.7)
+    part = torch.arange(n) // (n // P)
+    layouts = build_layouts(g, part, P)
+    assert layouts[0].recv_shape[2] == 0 and layouts[0].boundary[2].numel() == 0 and layouts[1].recv_shape == [1, None, 1]
+    setups = osetup.setup_world(dglpart.partition_graph(n, g.src, g.dst, part, P, g.feat, g.label, g.train_mask))
+    oargs, eargs = make_args(g, 4, n_epochs=3, n_hidden=8, **MODES[mode])
+    init = initial_state(oargs)
+    traces = run_world(setups, oargs, init_state=init)
+    trainer = LocalTrainer(layouts, eargs, LocalWorld(P, "cuda"), init_state=init)
+    for e in range(3):
+        for eng in trainer.engines:
+            eng.model.load_state_dict(traces[0].states[e])
+        losses = trainer.run_epoch(keep_logits=True)
+        for r, eng in enumerate(trainer.engines):
+            torch.testing.assert_close(eng.last_logits.cpu(), traces[r].logits[e], rtol=2e-4, atol=2e-4)
+            assert abs(float(losses[r].item()) - traces[r].losses[e]) <= 1e-4 * abs(traces[r].losses[e]) + 1e-5
