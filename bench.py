@@ -52,16 +52,17 @@ def parse():
     p.add_argument("--cpu-scale", type=int, default=16, help="CPU baseline runs on a 1/cpu-scale graph")
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--no-e2e", action="store_true")
+    p.add_argument("--use-pp", action="store_true", help="--use-pp of the reference scripts: layer-0 aggregate precomputed once")
     p.add_argument("--ncu-region", action="store_true", help="cudaProfilerStart/Stop around the timed steps")
     p.add_argument("--no-graph", action="store_true", help="launch every kernel from Python instead of replaying CUDA graphs")
     return p.parse_args()
 
 
-def engine_args(w, g, n_class, n_parts, dropout, cuda_graph=False):
+def engine_args(w, g, n_class, n_parts, dropout, cuda_graph=False, use_pp=False):
     return argparse.Namespace(
         model="graphsage", backend="nccl", dtype=w["dtype"], n_layers=w["n_layers"], n_hidden=w["n_hidden"],
         n_linear=0, n_feat=g.n_feat, n_class=n_class, n_train=int(g.train_mask.sum().item()), dropout=dropout,
-        norm="layer", lr=1e-2, weight_decay=0.0, use_pp=False, enable_pipeline=w["enable_pipeline"],
+        norm="layer", lr=1e-2, weight_decay=0.0, use_pp=use_pp, enable_pipeline=w["enable_pipeline"],
         feat_corr=w["feat_corr"], grad_corr=w["grad_corr"], corr_momentum=0.95, seed=0, n_epochs=0,
         log_every=10, n_partitions=n_parts, cuda_graph=cuda_graph)
 
@@ -209,7 +210,7 @@ def main():
         dist.all_reduce(hi, op=dist.ReduceOp.MAX)
         assert torch.equal(lo, hi), "ranks generated different synthetic graphs"
     layout = PartitionPlan(g, part, world_size).build(rank)
-    eargs = engine_args(w, g, n_class, world_size, args.dropout, cuda_graph=not args.no_graph)
+    eargs = engine_args(w, g, n_class, world_size, args.dropout, cuda_graph=not args.no_graph, use_pp=args.use_pp)
     engine = RankEngine(layout, eargs, world)
     n_nodes, n_edges = g.n_nodes, g.n_edges
     feat_host = layout.feat.to(engine.dtype).cpu().pin_memory()
@@ -342,7 +343,7 @@ def main():
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": w["dtype"], "data": "synthetic",
             "config": {"workload": f"{args.workload}: {w['desc']}", "n_nodes": n_nodes, "n_edges": n_edges,
-                       "partitions": world_size, "partition_method": "random", "dropout": args.dropout,
+                       "partitions": world_size, "partition_method": "random", "dropout": args.dropout, "use_pp": args.use_pp,
                        "n_in_rank0": layout.num_in, "halo_rank0": layout.num_all - layout.num_in,
                        "nnz_rank0": layout.nnz, "linear": ops.LINEAR_IMPL,
                        "l2": "per-epoch working set (features, activations, indices) exceeds the 126 MB L2; no flush",
