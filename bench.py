@@ -301,7 +301,6 @@ def main():
         ms_total = ms_eager_total * args.steps / n_eager
     else:
         ms_total = timed(args.steps, step)
-    clocks = sampler.stop() if sampler else None
     engine.buffer.check_status()
     launches = int(round(launches_per_step * args.steps))
     ms_step = ms_total / args.steps
@@ -333,6 +332,7 @@ def main():
                "h2d_bytes_per_step": int(feat_host.numel() * feat_host.element_size() + label_host.numel() * 8),
                "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e}
 
+    clocks = sampler.stop() if sampler else None      # sampled across the eager, replayed and end-to-end regions
     cb = None
     if rank == 0 and world_size == 1 and not args.no_cpu_baseline:
         cb = cpu_reference_run(w, args, steps=3, warmup=2)
