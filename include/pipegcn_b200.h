@@ -38,7 +38,8 @@ int pg_abi_version(void);
 const char* pg_last_error(void);
 /* writes sm major*10+minor, SM count and L2 bytes of `device`; needs a GPU */
 int pg_device_info(int device, int* sm_arch, int* sm_count, int64_t* l2_bytes);
-/* tuning knobs (process-wide): "agg_unroll" = 4 | 8 neighbour rows in flight per lane group */
+/* tuning knobs (process-wide): "agg_unroll" = 4 | 8 neighbour rows in flight per lane group;
+ * "agg_pack_short" = 0 | 1: two short rows per warp (16 lanes x 2 vectors) when the mean row length is < 12 */
 int pg_set_option(const char* name, int value);
 
 /* ------------------------------------------------------------------------------------------
@@ -60,6 +61,7 @@ typedef struct pg_csr {
   const int32_t* long_seg_ptr;  /* [n_long + 1] first segment of every long row */
   const int32_t* seg_long;      /* [n_seg] index into long_row */
   const int32_t* row_order;     /* [n_rows] processing order of the rows (e.g. by falling degree), or NULL */
+  int64_t nnz;                  /* number of entries (indptr[n_rows]); selects the short-row kernel shape */
 } pg_csr;
 
 /*

@@ -23,7 +23,7 @@ class PgError(RuntimeError):
 class pg_csr(C.Structure):
     _fields_ = [("indptr", C.c_void_p), ("indices", C.c_void_p), ("n_rows", C.c_int32), ("seg_len", C.c_int32),
                 ("n_long", C.c_int32), ("n_seg", C.c_int32), ("long_row", C.c_void_p), ("long_seg_ptr", C.c_void_p),
-                ("seg_long", C.c_void_p), ("row_order", C.c_void_p)]
+                ("seg_long", C.c_void_p), ("row_order", C.c_void_p), ("nnz", C.c_int64)]
 
 
 class pg_gemm_src(C.Structure):
@@ -78,7 +78,7 @@ def _load():
 
 
 lib, EXPORTS = _load()
-for _k, _v in (("agg_unroll", os.environ.get("PG_AGG_UNROLL")),):
+for _k, _v in (("agg_unroll", os.environ.get("PG_AGG_UNROLL")), ("agg_pack_short", os.environ.get("PG_AGG_PACK"))):
     if _v:
         lib.pg_set_option(_k.encode(), int(_v))
 

@@ -158,6 +158,7 @@ agg_fixup_kernel(pg_csr g, T* __restrict__ out, int64_t ldo, int nvec, const flo
 }
 
 int g_agg_unroll = 8;   // pg_set_option("agg_unroll", 4|8): neighbour rows in flight per group (VPL == 1)
+int g_agg_pack_short = 1;   // pg_set_option("agg_pack_short", 0|1): 16 lanes x 2 vectors per row when rows are short
 
 template <typename T, int VB, int G, int VPL, int U>
 static int launch_agg_u(const pg_csr& g, const T* x, int64_t ldx, T* out, int64_t ldo, int nvec,
@@ -197,6 +198,9 @@ static int dispatch_agg(const pg_csr& g, const T* x, int64_t ldx, T* out, int64_
   if (nvec <= 4) PG_AGG(4, 1);
   if (nvec <= 8) PG_AGG(8, 1);
   if (nvec <= 16) PG_AGG(16, 1);
+  // short rows (mean length < 12, e.g. the backward over a partition's halo rows): two rows per warp, each lane
+  // owning two 16-byte vectors, doubles the rows in flight for the same bytes per load instruction
+  if (nvec <= 32 && g_agg_pack_short && g.n_rows > 0 && g.nnz < 12 * static_cast<int64_t>(g.n_rows)) PG_AGG(16, 2);
   if (nvec <= 32) PG_AGG(32, 1);
   if (nvec <= 64) PG_AGG(32, 2);
   PG_AGG(32, 4);
@@ -287,6 +291,10 @@ extern "C" int pg_set_option(const char* name, int value) {
   if (strcmp(name, "agg_unroll") == 0) {
     PG_REQUIRE(value == 4 || value == 8, "agg_unroll must be 4 or 8");
     pg::g_agg_unroll = value;
+    return PG_OK;
+  }
+  if (strcmp(name, "agg_pack_short") == 0) {
+    pg::g_agg_pack_short = value ? 1 : 0;
     return PG_OK;
   }
   pg::set_error("pg_set_option: unknown option '%s'", name);

@@ -53,7 +53,7 @@ class CsrPlan:
         self.c = _C.pg_csr(self.indptr.data_ptr(), self.indices.data_ptr(), self.n_rows, self.seg_len, n_long,
                            self.n_seg, self.long_row.data_ptr(), self.long_seg_ptr.data_ptr(),
                            self.seg_long.data_ptr(),
-                           self.row_order.data_ptr() if self.row_order is not None else None)
+                           self.row_order.data_ptr() if self.row_order is not None else None, self.nnz)
 
     def scratch(self, d: int) -> Optional[torch.Tensor]:
         if self.n_seg == 0:
