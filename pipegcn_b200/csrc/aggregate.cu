@@ -158,7 +158,8 @@ agg_fixup_kernel(pg_csr g, T* __restrict__ out, int64_t ldo, int nvec, const flo
 }
 
 int g_agg_unroll = 8;   // pg_set_option("agg_unroll", 4|8): neighbour rows in flight per group (VPL == 1)
-int g_agg_pack_short = 1;   // pg_set_option("agg_pack_short", 0|1): 16 lanes x 2 vectors per row when rows are short
+int g_agg_pack_short = 0;   // pg_set_option("agg_pack_short", 0|1): 16 lanes x 2 vectors per row when rows are short.
+                            // OFF: measured slower (tools/agg_micro.py, P=8 partition: bwd 277 -> 312 us)
 
 template <typename T, int VB, int G, int VPL, int U>
 static int launch_agg_u(const pg_csr& g, const T* x, int64_t ldx, T* out, int64_t ldo, int nvec,
