@@ -110,3 +110,49 @@ def test_metis_partition_is_valid_and_balanced():
         lays = build_layouts(g, part, 3)
         assert sum(l.num_in for l in lays) == g.n_nodes
         assert sum(l.nnz for l in lays) == g.n_edges
+
+
+def _syncbn_worker(rank, size, port, out_dir):
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    import torch.distributed as dist
+    dist.init_process_group("gloo", rank=rank, world_size=size)
+    from pipegcn_b200.module.sync_bn import SyncBatchNorm
+    torch.manual_seed(0)
+    x_all = torch.randn(40, 6) * 2 + 1
+    g_all = torch.randn(40, 6)
+    rows = slice(0, 17) if rank == 0 else slice(17, 40)
+    bn = SyncBatchNorm(6, whole_size=40)
+    with torch.no_grad():
+        bn.weight.copy_(torch.linspace(0.5, 1.5, 6))
+        bn.bias.copy_(torch.linspace(-1, 1, 6))
+    x = x_all[rows].clone().requires_grad_(True)
+    y = bn(x)
+    y.backward(g_all[rows])
+    torch.save({"y": y.detach(), "dx": x.grad, "dw": bn.weight.grad, "db": bn.bias.grad,
+                "rm": bn.running_mean.clone(), "rv": bn.running_var.clone()}, f"{out_dir}/bn{rank}.pt")
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_sync_batch_norm_equals_batch_norm_on_all_rows():
+    """--norm batch (module/sync_bn.py): two partitions with synchronised statistics == BatchNorm1d over all rows
+    (biased variance, momentum update of the running statistics with the biased variance as the reference does)."""
+    size = 2
+    out_dir = tempfile.mkdtemp(prefix="pg_gloo_")
+    mp.spawn(_syncbn_worker, args=(size, _free_port(), out_dir), nprocs=size, join=True)
+    torch.manual_seed(0)
+    x_all = (torch.randn(40, 6) * 2 + 1).requires_grad_(True)
+    g_all = torch.randn(40, 6)
+    w = torch.linspace(0.5, 1.5, 6).requires_grad_(True)
+    b = torch.linspace(-1, 1, 6).requires_grad_(True)
+    mean, var = x_all.mean(0), x_all.var(0, unbiased=False)
+    y = (x_all - mean) / torch.sqrt(var + 1e-5) * w + b
+    y.backward(g_all)
+    got = [torch.load(f"{out_dir}/bn{r}.pt", weights_only=False) for r in range(size)]
+    torch.testing.assert_close(torch.cat([got[0]["y"], got[1]["y"]]), y.detach(), rtol=1e-4, atol=1e-5)
+    torch.testing.assert_close(torch.cat([got[0]["dx"], got[1]["dx"]]), x_all.grad, rtol=1e-4, atol=1e-5)
+    for r in range(size):            # parameter gradients are already summed over ranks (sync_bn.py:35-36)
+        torch.testing.assert_close(got[r]["dw"], w.grad, rtol=1e-4, atol=1e-5)
+        torch.testing.assert_close(got[r]["db"], b.grad, rtol=1e-4, atol=1e-5)
+        torch.testing.assert_close(got[r]["rm"], 0.1 * mean.detach(), rtol=1e-4, atol=1e-6)
+        torch.testing.assert_close(got[r]["rv"], 0.9 + 0.1 * var.detach(), rtol=1e-4, atol=1e-6)

@@ -104,3 +104,22 @@ def test_ops_refuse_cpu_tensors():
     from pipegcn_b200 import _C, ops
     with pytest.raises(_C.PgError):
         ops._rows(torch.zeros(4, 4))
+
+
+def test_command_line_matches_reference_flags():
+    """Same flags, aliases and defaults as /root/reference/helper/parser.py (fixture tests/golden/ref_parser.json),
+    except `--backend` (nccl instead of gloo: the only implemented transport) and the added `--dtype`."""
+    import json
+    from pipegcn_b200.helper.parser import create_parser
+    ref = json.loads((ROOT / "tests" / "golden" / "ref_parser.json").read_text())
+    ours = vars(create_parser([]))
+    for k, v in ref["defaults"].items():
+        assert k in ours, f"flag {k} missing"
+        if k != "backend":
+            assert ours[k] == v, (k, ours[k], v)
+    assert ours["backend"] == "nccl" and ours["dtype"] == "fp32"
+    assert set(ours) - set(ref["defaults"]) == {"dtype"}
+    got = vars(create_parser(["--n_layers", "4", "--enable_pipeline", "--feat-corr", "--no-eval", "--norm", "batch"]))
+    for k, v in ref["parsed_example"].items():
+        if k != "backend":
+            assert got[k] == v, (k, got[k], v)
