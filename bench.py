@@ -8,7 +8,9 @@
 Workload (BASELINE.json configs[1]): synthetic RMAT 1 M nodes / 20 M edges, one partition per GPU
 (random partition), 3-layer GraphSAGE, hidden 256, bf16 activations, --enable-pipeline.  A step is one
 epoch: forward, loss, backward (with the gradient halo exchange), gradient all-reduce, Adam step.
-One JSON line is printed by rank 0.
+After the warm-up a short Python-launched region is instrumented with CUDA events (roofline of the aggregate kernel,
+exposed communication); the timed region proper replays whole epochs from CUDA graphs (`--no-graph`: launches every
+kernel from Python).  One JSON line is printed by rank 0.
 """
 from __future__ import annotations
 

@@ -1,10 +1,11 @@
 // Dense part of the GraphSAGE layer on the 5th-generation tensor cores:
 //
-//   C[M,N] = A0[M,K0] * B0[N,K0]^T  (+ A1[M,K1] * B1[N,K1]^T)  (+ bias[N])  (/ row_div[M])
+//   C[M,N] = sum_s A_s[M,K_s] * B_s[N,K_s]^T  (+ bias[N])  (/ row_div[M])          1 <= s <= 6 operand pairs
 //
 // i.e. `linear1(feat[:N_in]) + linear2(ah)` of /root/reference/module/layer.py:51 as ONE kernel
-// (A0 = inner rows, A1 = neighbour mean, B = the two weight matrices, bias = b1 + b2), and with a
-// single source the dX GEMMs of its backward (row_div = in_deg fuses the `/ degs` gradient).
+// (pair 0 = inner rows x W1, pair 1 = neighbour mean x W2, bias = b1 + b2), with a single pair the dX
+// GEMMs of its backward (row_div = in_deg fuses the `/ degs` gradient), and with three pairs per product
+// the split-fp32 "3xTF32" evaluation (hi*hi + hi*lo + lo*hi) used for fp32 activations.
 //
 // Persistent, warp-specialised, sm_100a only:
 //   warp 0    TMA producer: 128-byte-swizzled K-major tiles of A (128 rows) and B (n_pad rows)
@@ -13,8 +14,8 @@
 //             fp32 accumulators live in TMEM, two accumulator stages so that the epilogue of tile
 //             i overlaps the MMAs of tile i+1
 //   warp 2    allocates / frees TMEM
-//   warps 4-7 epilogue: tcgen05.ld 32 lanes x 32 columns per warp, bias / row scale, convert,
-//             16-byte global stores (each thread owns one output row)
+//   warps 4-7 epilogue: tcgen05.ld (32 lanes x 16 columns), bias / row scale, convert, 128B-swizzled
+//             shared-memory slab, TMA store (cp.async.bulk.tensor) -- every global write is a full line
 // M is tiled by 128 (TMA zero-fills the tail, the epilogue masks it); N <= 256 is one tile
 // (padded to a multiple of 16 with zero-filled weight rows); K tails are zero-filled by TMA.
 #include <cuda.h>
