@@ -22,8 +22,6 @@ if __name__ == '__main__':
     if args.graph_name == '':
         args.graph_name = '%s-%d-%s-%s-%s' % (args.dataset, args.n_partitions, args.partition_method,
                                               args.partition_obj, 'induc' if args.inductive else 'trans')
-    if args.inductive:
-        raise NotImplementedError('--inductive: the train-subgraph split is outside the hot path built so far')
     print(args)
     if args.backend not in ('nccl', 'nvlink'):
         # the reference raises for everything but gloo (main.py:60-65); this engine is NVLink/NCCL only

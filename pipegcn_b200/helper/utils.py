@@ -13,7 +13,7 @@ import warnings
 import torch
 
 from ..partition import PartitionPlan, get_layer_size  # noqa: F401  (re-export)
-from ..synthetic import SHAPES, make_graph, random_partition
+from ..synthetic import SHAPES, make_graph, random_partition, train_subgraph
 
 _ALIAS = {'reddit': 'reddit-shaped', 'ogbn-products': 'products-shaped'}
 _cache = {}
@@ -55,5 +55,7 @@ def load_partition(args, rank, device=None):
     g, n_feat, n_class = load_data(args.dataset, device=device)
     args.n_feat, args.n_class = n_feat, n_class
     args.n_train = int(g.train_mask.sum().item())
+    if getattr(args, 'inductive', False):          # main.py:34-35: partition the train-node subgraph
+        g = train_subgraph(g)
     part = graph_partition(g, args)
     return PartitionPlan(g, part, args.n_partitions).build(rank)

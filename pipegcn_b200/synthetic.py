@@ -130,3 +130,15 @@ def random_partition(n_nodes: int, n_parts: int, seed: int = 1, device="cpu") ->
     if n_nodes >= n_parts:
         part[:n_parts] = torch.arange(n_parts, device=device)
     return part
+
+
+def train_subgraph(g: GlobalGraph) -> GlobalGraph:
+    """`--inductive`: the graph induced by the training nodes (`g.subgraph(g.ndata['train_mask'])`,
+    /root/reference/main.py:34-35, helper/utils.py:226-230); node ids are compacted in ascending order."""
+    keep = g.train_mask
+    new_id = torch.full((g.n_nodes,), -1, dtype=torch.int64, device=g.src.device)
+    n = int(keep.sum().item())
+    new_id[keep] = torch.arange(n, dtype=torch.int64, device=g.src.device)
+    em = keep[g.src] & keep[g.dst]
+    return GlobalGraph(n, new_id[g.src[em]], new_id[g.dst[em]], g.feat[keep], g.label[keep],
+                       torch.ones(n, dtype=torch.bool, device=g.src.device))

@@ -77,3 +77,22 @@ def test_layout_equals_reference_procedure(n, m, p, seed):
         assert L.recv_shape == S.recv_shape
         for a, b in zip(L.boundary, S.boundary):
             assert (a is None and b is None) or torch.equal(a, b)
+
+
+def test_inductive_train_subgraph():
+    """--inductive (main.py:34-35): only train nodes and the edges among them survive; every node is a train node."""
+    from pipegcn_b200.synthetic import train_subgraph
+    g = random_graph(50, 300, 3)
+    s = train_subgraph(g)
+    n = int(g.train_mask.sum())
+    assert s.n_nodes == n and bool(s.train_mask.all()) and s.feat.shape[0] == n
+    keep = g.train_mask
+    assert s.n_edges == int((keep[g.src] & keep[g.dst]).sum())
+    old = torch.nonzero(keep).flatten()
+    assert torch.equal(s.feat, g.feat[old]) and torch.equal(s.label, g.label[old])
+    # edges map back to original train-train edges
+    back = set(zip(old[s.src].tolist(), old[s.dst].tolist()))
+    orig = {(a, b) for a, b in zip(g.src.tolist(), g.dst.tolist()) if keep[a] and keep[b]}
+    assert back == orig
+    lays = build_layouts(s, torch.arange(n) % 2, 2)
+    assert sum(l.num_in for l in lays) == n and all(bool(l.train_mask.all()) for l in lays)
