@@ -5,16 +5,20 @@
         bench.py --gpus N --steps K --warmup W
     python bench.py --impl reference ...      # the CPU path (oracle port of the reference) on the host cores
 
-Workload (BASELINE.json configs[1]): synthetic RMAT 1 M nodes / 20 M edges, one partition per GPU
+Default workload (BASELINE.json configs[1]): synthetic RMAT 1 M nodes / 20 M edges, one partition per GPU
 (random partition), 3-layer GraphSAGE, hidden 256, bf16 activations, --enable-pipeline.  A step is one
 epoch: forward, loss, backward (with the gradient halo exchange), gradient all-reduce, Adam step.
-After the warm-up a short Python-launched region is instrumented with CUDA events (roofline of the aggregate kernel,
-exposed communication); the timed region proper replays whole epochs from CUDA graphs (`--no-graph`: launches every
-kernel from Python).  One JSON line is printed by rank 0.
+
+Order of a run: set-up -> (N > 1) parity of the real multi-GPU path against the CPU oracle -> warm-up -> a short
+Python-launched region instrumented with CUDA events (roofline of the aggregate kernel) -> the timed region: K epochs
+replayed from CUDA graphs (`--no-graph`: launched from Python), exposed communication accumulated ON THE DEVICE by the
+flag-wait kernel inside that region -> the end-to-end region (host buffers, H2D + D2H per step) -> (N = 1) the CPU
+baseline -> ONE JSON line from rank 0.  The process returns normally (no os._exit).
 """
 from __future__ import annotations
 
 import argparse
+import gc
 import json
 import os
 import subprocess
@@ -31,13 +35,25 @@ if str(ROOT) not in sys.path:
 import torch  # noqa: E402
 
 WORKLOADS = {
+    # BASELINE.json configs[1]
     "rmat-1m": dict(shape="rmat-1m", n_layers=3, n_hidden=256, dtype="bf16", enable_pipeline=True,
                     feat_corr=False, grad_corr=False,
                     desc="RMAT 1M nodes / 20M edges, F=256, C=64, 3-layer GraphSAGE hidden 256, bf16, --enable-pipeline"),
+    # configs[2] (layers as scripts/reddit.sh:8)
     "reddit-shaped": dict(shape="reddit-shaped", n_layers=4, n_hidden=256, dtype="fp32", enable_pipeline=True,
                           feat_corr=True, grad_corr=True,
                           desc="Reddit-shaped RMAT 233K nodes / 115M edges, F=602, C=41, 4-layer GraphSAGE hidden 256, "
                                "fp32, --enable-pipeline --feat-corr --grad-corr"),
+    # configs[3]: no pipeline -> the exchange is waited for in the epoch that needs it
+    "products-shaped": dict(shape="products-shaped", n_layers=3, n_hidden=128, dtype="fp32", enable_pipeline=False,
+                            feat_corr=False, grad_corr=False,
+                            desc="ogbn-products-shaped RMAT 2.4M nodes / 62M edges, F=100, C=47, 3-layer GraphSAGE "
+                                 "hidden 128, fp32, no pipeline"),
+    # configs[4]: per-rank graph construction (no rank holds the global edge list), see pipegcn_b200/distgraph.py
+    "papers100m-shaped": dict(shape="papers100m-shaped", n_layers=3, n_hidden=128, dtype="bf16", enable_pipeline=True,
+                              feat_corr=False, grad_corr=False, distributed_build=True,
+                              desc="ogbn-papers100M-shaped RMAT 111M nodes / 1.6B edges, F=128, C=172, 3-layer GraphSAGE "
+                                   "hidden 128, bf16, --enable-pipeline, per-rank graph construction"),
     "small": dict(shape="small", n_layers=3, n_hidden=64, dtype="bf16", enable_pipeline=True,
                   feat_corr=False, grad_corr=False, desc="20K-node RMAT (debug)"),
 }
@@ -51,19 +67,23 @@ def parse():
     p.add_argument("--impl", choices=["ours", "reference"], default="ours")
     p.add_argument("--workload", default="rmat-1m", choices=list(WORKLOADS))
     p.add_argument("--dropout", type=float, default=0.5, help="reference default (helper/parser.py:14)")
-    p.add_argument("--cpu-scale", type=int, default=16, help="CPU baseline runs on a 1/cpu-scale graph")
+    p.add_argument("--partition-method", default="random", choices=["random", "metis"])
+    p.add_argument("--partition-obj", default="vol", choices=["vol", "cut"])
+    p.add_argument("--scale-down", type=int, default=1, help="1/k nodes and edges of the named shape (debug, stated in config)")
+    p.add_argument("--cpu-full", action="store_true", help="cpu_baseline leg: time the full graph instead of the bounded sample")
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--no-e2e", action="store_true")
+    p.add_argument("--no-parity", action="store_true", help="skip the multi-GPU parity check before timing (N > 1)")
     p.add_argument("--use-pp", action="store_true", help="--use-pp of the reference scripts: layer-0 aggregate precomputed once")
-    p.add_argument("--ncu-region", action="store_true", help="cudaProfilerStart/Stop around the timed steps")
+    p.add_argument("--ncu-region", action="store_true", help="cudaProfilerStart/Stop around the instrumented steps")
     p.add_argument("--no-graph", action="store_true", help="launch every kernel from Python instead of replaying CUDA graphs")
     return p.parse_args()
 
 
-def engine_args(w, g, n_class, n_parts, dropout, cuda_graph=False, use_pp=False):
+def engine_args(w, n_feat, n_class, n_train, n_parts, dropout, cuda_graph=False, use_pp=False):
     return argparse.Namespace(
         model="graphsage", backend="nccl", dtype=w["dtype"], n_layers=w["n_layers"], n_hidden=w["n_hidden"],
-        n_linear=0, n_feat=g.n_feat, n_class=n_class, n_train=int(g.train_mask.sum().item()), dropout=dropout,
+        n_linear=0, n_feat=n_feat, n_class=n_class, n_train=n_train, dropout=dropout,
         norm="layer", lr=1e-2, weight_decay=0.0, use_pp=use_pp, enable_pipeline=w["enable_pipeline"],
         feat_corr=w["feat_corr"], grad_corr=w["grad_corr"], corr_momentum=0.95, seed=0, n_epochs=0,
         log_every=10, n_partitions=n_parts, cuda_graph=cuda_graph)
@@ -114,52 +134,89 @@ def peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def shape_spec(w, scale_down=1):
+    from pipegcn_b200.synthetic import SHAPES
+    spec = dict(SHAPES[w["shape"]])
+    if scale_down > 1:
+        spec["n_nodes"] //= scale_down
+        spec["n_edges"] //= scale_down
+    return spec
+
+
 # ----------------------------------------------------------------------------------------------- CPU arm
-def cpu_reference_run(w, args, steps, warmup):
-    """The reference's algorithm on the host cores: oracle port, one partition, bounded 1/scale sample."""
+def cpu_reference_run(w, args, steps, warmup, full=True):
+    """The reference's algorithm on the host cores: the oracle port (torch CPU + C/OpenMP SpMM), ONE partition, on
+    the FULL graph of the workload (`full`) or on a stated 1/16 sample (the in-run `cpu_baseline` leg, bounded to
+    ~30 s).  Nothing is extrapolated: `value` is epochs/s of exactly the graph named in `sample`."""
     from oracle import dglpart
     from oracle import setup as osetup
+    from oracle.cbuild import set_threads
     from oracle.fabric import ThreadFabric
     from oracle.train import OracleArgs, run_rank
-    from pipegcn_b200.synthetic import SHAPES, make_graph
-    spec = dict(SHAPES[w["shape"]])
-    scale = max(1, args.cpu_scale)
-    spec["n_nodes"] //= scale
-    spec["n_edges"] //= scale
-    from oracle.cbuild import set_threads
+    from pipegcn_b200.synthetic import make_graph
     n_cpu = os.cpu_count() or 1
-    g = make_graph(spec, device="cpu")
-    part = torch.zeros(g.n_nodes, dtype=torch.int64)
-    parts = dglpart.partition_graph(g.n_nodes, g.src, g.dst, part, 1, g.feat, g.label, g.train_mask)
-    setups = osetup.setup_world(parts)
-    n_ep = warmup + steps
-    oargs = OracleArgs(n_layers=w["n_layers"], n_hidden=w["n_hidden"], n_feat=g.n_feat, n_class=spec["n_class"],
-                       n_train=int(g.train_mask.sum()), dropout=args.dropout, n_epochs=n_ep,
-                       enable_pipeline=w["enable_pipeline"], feat_corr=w["feat_corr"], grad_corr=w["grad_corr"])
-    # all the host threads it can USE: on many-core hosts the fastest setting is below the core count, so one
-    # epoch is timed at a few thread counts first and the fastest is kept
+    base_scale = max(1, args.scale_down)
+
+    def world(scale):
+        g = make_graph(shape_spec(w, scale), device="cpu")
+        part = torch.zeros(g.n_nodes, dtype=torch.int64)
+        parts = dglpart.partition_graph(g.n_nodes, g.src, g.dst, part, 1, g.feat, g.label, g.train_mask)
+        oargs = OracleArgs(n_layers=w["n_layers"], n_hidden=w["n_hidden"], n_feat=g.n_feat,
+                           n_class=shape_spec(w)["n_class"], n_train=int(g.train_mask.sum()), dropout=args.dropout,
+                           n_epochs=2, enable_pipeline=w["enable_pipeline"], feat_corr=w["feat_corr"],
+                           grad_corr=w["grad_corr"])
+        return g, osetup.setup_world(parts), oargs
+
+    # thread count: on many-core hosts the fastest setting is below the core count; probe on a 1/16 sample
+    probe_scale = base_scale * 16
+    g_s, setups_s, oargs_s = world(probe_scale)
     cand = sorted({t for t in (8, 16, 32, 64, n_cpu) if t <= n_cpu})
-    probe = OracleArgs(**{**oargs.__dict__, "n_epochs": 2})
     best = None
     for t in cand:
         set_threads(t)
-        w1 = run_rank(setups[0], probe, ThreadFabric(1), keep_trace=False).wall[-1]
+        w1 = run_rank(setups_s[0], oargs_s, ThreadFabric(1), keep_trace=False).wall[-1]
         if best is None or w1 < best[0]:
             best = (w1, t)
     cores = best[1]
     set_threads(cores)
+    if full:
+        del g_s, setups_s
+        gc.collect()
+        g, setups, oargs = world(base_scale)
+        scale_txt = "the FULL graph of the workload" if base_scale == 1 else f"the 1/{base_scale}-scale graph this run uses"
+    else:
+        g, setups, oargs = g_s, setups_s, oargs_s
+        scale_txt = f"a 1/{probe_scale}-scale sample of the workload's graph (bounded leg; NOT extrapolated)"
+    oargs = OracleArgs(**{**oargs.__dict__, "n_epochs": warmup + steps})
     tr = run_rank(setups[0], oargs, ThreadFabric(1), keep_trace=False)
     per_epoch = sum(tr.wall[warmup:]) / max(len(tr.wall[warmup:]), 1)
-    eps_sample = 1.0 / max(per_epoch, 1e-9)
     return {
-        "value": eps_sample / scale, "unit": "epochs/s", "cores": cores, "kind": "port",
-        "sample": (f"oracle (CPU port of the reference, torch {torch.__version__}, {cores} of {n_cpu} host threads -- the "
-                   f"fastest of {cand}) on a 1/{scale}-scale "
-                   f"graph of the same shape ({g.n_nodes} nodes, {g.n_edges} edges, 1 partition), {steps} epochs after "
-                   f"{warmup} warm-up: {eps_sample:.3f} epochs/s on the sample; value = that / {scale} "
-                   f"(linear-in-edges equivalent for the full graph)"),
-        "sample_epochs_per_s": eps_sample,
+        "value": 1.0 / max(per_epoch, 1e-9), "unit": "epochs/s", "cores": cores, "kind": "port",
+        "sample": (f"oracle (CPU port of the reference: torch {torch.__version__} CPU kernels + C/OpenMP SpMM, fp32), "
+                   f"{cores} of {n_cpu} host threads (fastest of {cand} on a 1/{probe_scale} sample), 1 partition, on "
+                   f"{scale_txt}: {g.n_nodes} nodes, {g.n_edges} edges, {steps} timed epochs after {warmup} warm-up"),
+        "n_nodes": g.n_nodes, "n_edges": g.n_edges, "steps": steps, "warmup": warmup,
     }
+
+
+def teardown(world_size, engine_holder):
+    """Leave like a library user would: drop the captured graphs (they hold NCCL kernels), free the engine, destroy
+    the process group, return.  A watchdog only fires if communicator teardown hangs."""
+    import torch.distributed as dist
+    dog = threading.Timer(90.0, lambda: (sys.stderr.write("[bench] teardown watchdog fired\n"), os._exit(0)))
+    dog.daemon = True
+    dog.start()
+    eng = engine_holder.pop("engine", None)
+    if eng is not None:
+        eng.graphs = None
+        del eng
+    gc.collect()
+    torch.cuda.synchronize()
+    if world_size > 1 and dist.is_initialized():
+        dist.barrier()
+        torch.cuda.synchronize()
+        dist.destroy_process_group()
+    dog.cancel()
 
 
 def main():
@@ -172,13 +229,23 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return
-        steps, warmup = max(1, min(args.steps, 4)), max(1, min(args.warmup, 2))
-        cb = cpu_reference_run(w, args, steps, warmup)
+        steps, warmup = max(1, args.steps), max(0, args.warmup)
+        # the whole run has to end within the driver's limit: ~20 s per full-graph epoch on rmat-1m -> cap the epochs
+        budget = int(os.environ.get("PG_REF_MAX_EPOCHS", "12"))
+        note = None
+        if steps + warmup > budget:
+            warmup = min(warmup, 2)
+            steps = max(1, budget - warmup)
+            note = f"asked for --steps {args.steps} --warmup {args.warmup}; ran {steps} + {warmup} full-graph epochs (time bound)"
+        cb = cpu_reference_run(w, args, steps, warmup, full=True)
         line = {"impl": "reference", "metric": "epochs_per_sec", "value": cb["value"], "unit": "epochs/s",
                 "n_gpus": args.gpus, "steps": steps, "warmup": warmup, "ms_per_step": 1e3 / cb["value"],
                 "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
                 "data": "synthetic",
-                "config": {"workload": f"{args.workload}: {w['desc']}", "partitions": 1, "dropout": args.dropout},
+                "config": {"workload": f"{args.workload}: {w['desc']}", "n_nodes": cb["n_nodes"], "n_edges": cb["n_edges"],
+                           "partitions": 1, "partitions_note": "the CPU arm runs ONE partition at every --gpus N "
+                           "(all host threads in one process; splitting it over gloo processes shares the same cores)",
+                           "dropout": args.dropout, "steps_note": note},
                 "cpu_baseline": cb,
                 "e2e": {"value": cb["value"], "unit": "epochs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
         print(json.dumps(line), flush=True)
@@ -190,7 +257,7 @@ def main():
     import torch.distributed as dist
     from pipegcn_b200 import _C, ops
     from pipegcn_b200.partition import PartitionPlan
-    from pipegcn_b200.synthetic import SHAPES, make_graph, random_partition
+    from pipegcn_b200.synthetic import make_graph, random_partition
     from pipegcn_b200.train import RankEngine
     from pipegcn_b200.world import DistWorld, LocalWorld
 
@@ -201,23 +268,51 @@ def main():
         world = LocalWorld(1, dev).view(0)
     assert args.gpus == world_size, f"--gpus {args.gpus} but WORLD_SIZE={world_size}"
 
+    # ---- real multi-GPU parity (CUDA IPC + NVLink pushes + NCCL + graph replay) against the CPU oracle, before timing
+    parity = None
+    if world_size > 1 and not args.no_parity:
+        from tools.dist_parity import check_world
+        parity = check_world(world, dev, shapes=("tiny", "small"), modes=("pipeline_corr",), graph_modes=(False, True))
+        if rank == 0 and not parity["ok"]:
+            print(f"[bench] multi-GPU parity FAILED: {parity}", file=sys.stderr)
+
     t_setup = time.time()
-    g = make_graph(w["shape"], device=dev)
-    n_class = SHAPES[w["shape"]]["n_class"]
-    part = random_partition(g.n_nodes, world_size, seed=1, device=dev)
-    if world_size > 1:   # every rank built the graph itself; make sure they agree
-        chk = torch.stack([g.src.sum(), g.dst.sum(), part.sum(), g.train_mask.sum()]).to(torch.float64)
-        lo, hi = chk.clone(), chk.clone()
-        dist.all_reduce(lo, op=dist.ReduceOp.MIN)
-        dist.all_reduce(hi, op=dist.ReduceOp.MAX)
-        assert torch.equal(lo, hi), "ranks generated different synthetic graphs"
-    layout = PartitionPlan(g, part, world_size).build(rank)
-    eargs = engine_args(w, g, n_class, world_size, args.dropout, cuda_graph=not args.no_graph, use_pp=args.use_pp)
+    spec = shape_spec(w, args.scale_down)
+    n_class = spec["n_class"]
+    if w.get("distributed_build"):
+        from pipegcn_b200.distgraph import build_rank_layout
+        layout, ginfo = build_rank_layout(spec, rank, world_size, dev, world)
+        n_nodes, n_edges, n_feat, n_train = ginfo["n_nodes"], ginfo["n_edges"], spec["n_feat"], ginfo["n_train"]
+        part_method = "random (hash of the node id; per-rank construction)"
+    else:
+        g = make_graph(spec, device=dev)
+        if args.partition_method == "random" or world_size == 1:
+            part = random_partition(g.n_nodes, world_size, seed=1, device=dev)
+        else:
+            from pipegcn_b200.helper.utils import graph_partition
+            pargs = argparse.Namespace(partition_method="metis", partition_obj=args.partition_obj, n_partitions=world_size,
+                                       dataset=f"synthetic:{w['shape']}" + (f"-div{args.scale_down}" if args.scale_down > 1 else ""),
+                                       graph_name="", inductive=False, partition_cache=True, skip_partition=False)
+            part = graph_partition(g, pargs, rank)
+        if world_size > 1:   # every rank built the graph itself; make sure they agree
+            chk = torch.stack([g.src.sum(), g.dst.sum(), part.sum(), g.train_mask.sum()]).to(torch.float64)
+            lo, hi = chk.clone(), chk.clone()
+            dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+            dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+            assert torch.equal(lo, hi), "ranks generated different synthetic graphs"
+        layout = PartitionPlan(g, part, world_size).build(rank)
+        n_nodes, n_edges, n_feat, n_train = g.n_nodes, g.n_edges, g.n_feat, int(g.train_mask.sum().item())
+        part_method = args.partition_method if world_size > 1 else "none (1 partition)"
+        del g, part
+    eargs = engine_args(w, n_feat, n_class, n_train, world_size, args.dropout, cuda_graph=not args.no_graph,
+                        use_pp=args.use_pp)
     engine = RankEngine(layout, eargs, world)
-    n_nodes, n_edges = g.n_nodes, g.n_edges
+    holder = {"engine": engine}
     feat_host = layout.feat.to(engine.dtype).cpu().pin_memory()
     label_host = engine.labels.cpu().pin_memory()
-    del g
+    layout_info = dict(n_in=layout.num_in, halo=layout.num_all - layout.num_in, nnz=layout.nnz)
+    del layout
+    gc.collect()
     torch.cuda.empty_cache()
     setup_s = time.time() - t_setup
 
@@ -227,6 +322,12 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    def max_over_ranks(x):
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        if world_size > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
     def timed(n_steps, fn):
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -235,17 +336,12 @@ def main():
             fn()
         e1.record()
         barrier()
-        ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
-        if world_size > 1:
-            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-        return float(ms.item())
+        return max_over_ranks(e0.elapsed_time(e1))
 
     def step():
-        engine.buffer.timer.clear()
         engine.run_epoch()
 
     def step_e2e():
-        engine.buffer.timer.clear()
         engine.set_features(feat_host)
         engine.labels.copy_(label_host, non_blocking=True)
         loss = engine.run_epoch()
@@ -255,32 +351,23 @@ def main():
         step()
     engine.buffer.check_status()
 
-    # ---- instrumented eager epochs: every aggregate launch bracketed by CUDA events (roofline), the flag waits
-    #      bracketed by CUDA events (exposed communication); kernels are launched from Python here
+    # ---- instrumented eager epochs: every aggregate launch bracketed by CUDA events (roofline)
     ops.PROFILE = []
     _C.LAUNCHES = 0
-    comm_s = []
     n_eager = args.steps if args.no_graph else min(args.steps, 5)
     sampler = ClockSampler(local_rank) if rank == 0 else None
     if sampler:
         sampler.start()
-
-    def step_prof():
-        engine.buffer.timer.clear()
-        engine.run_epoch()
-        comm_s.append(engine.buffer.timer)      # events resolved after the region
-        engine.buffer.timer = type(engine.buffer.timer)()
-
+    engine.buffer.take_wait_ns()
     if args.ncu_region:
         torch.cuda.cudart().cudaProfilerStart()
-    ms_eager_total = timed(n_eager, step_prof)
+    ms_eager_total = timed(n_eager, step)
     if args.ncu_region:
         torch.cuda.cudart().cudaProfilerStop()
     launches_per_step = _C.LAUNCHES / max(n_eager, 1)
     prof, ops.PROFILE = ops.PROFILE, None
     engine.buffer.check_status()
-    exposed = [t.tot_time() for t in comm_s]
-    exposed_s = sum(exposed) / max(len(exposed), 1)
+    eager_wait_s = engine.buffer.take_wait_ns() / 1e9 / max(n_eager, 1)
     ms_eager = ms_eager_total / n_eager
 
     # ---- timed region proper: K epochs replayed from CUDA graphs (one graph per epoch parity)
@@ -297,13 +384,15 @@ def main():
             ops.STEP_DEV = None
             graph_info = {"enabled": False, "error": f"{type(e).__name__}: {str(e)[:200]}"}
             print(f"[bench] CUDA graph capture failed, timing eager launches: {e}", file=sys.stderr)
-    if graph_info["enabled"]:
+    engine.buffer.take_wait_ns()
+    if graph_info["enabled"] or not args.no_graph:
         ms_total = timed(args.steps, step)
-    elif args.no_graph:
-        ms_total = ms_eager_total * args.steps / n_eager
+        wait_s = engine.buffer.take_wait_ns() / 1e9 / args.steps
     else:
-        ms_total = timed(args.steps, step)
+        ms_total = ms_eager_total * args.steps / n_eager
+        wait_s = eager_wait_s
     engine.buffer.check_status()
+    exposed_s = max_over_ranks(wait_s)
     launches = int(round(launches_per_step * args.steps))
     ms_step = ms_total / args.steps
     value = 1e3 / ms_step
@@ -314,16 +403,21 @@ def main():
     agg_bytes = sum(nb for _, _, nb in prof)
     n_agg = len(prof)
     achieved = (agg_bytes / 1e9) / (agg_ms / 1e3) if agg_ms > 0 else 0.0
-    traffic = None
+    traffic, traffic_src = None, None
     tf = ROOT / "profiles" / "agg_traffic.json"
-    if tf.exists():       # per-launch DRAM bytes of the aggregate kernel from the committed `ncu --set full` capture
-        traffic = json.loads(tf.read_text()).get(f"{args.workload}:{world_size}")
+    if tf.exists():       # per-launch DRAM bytes of the aggregate kernel from the committed `ncu --set full` captures
+        ent = json.loads(tf.read_text()).get(f"{args.workload}:{world_size}")
+        if isinstance(ent, dict):
+            traffic, traffic_src = ent.get("bytes"), ent.get("source")
+        else:
+            traffic = ent
     roofline = {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                "traffic": traffic, "kernel": "pg::agg_kernel (+fix-up), forward and backward aggregate",
+                "traffic": traffic, "traffic_source": traffic_src,
+                "kernel": "pg::agg2_kernel (+fix-up), forward and backward aggregate",
                 "launches": n_agg, "avg_launch_ms": agg_ms / max(n_agg, 1),
                 "algorithmic_bytes_per_launch": agg_bytes / max(n_agg, 1),
                 "share_of_step": agg_ms / ms_eager_total if ms_eager_total else None, "peak_source": peak_src,
-                "measured_in": f"{n_eager} eager (Python-launched) epochs before the graph-replayed timed region"}
+                "measured_in": f"{n_eager} eager (Python-launched) epochs before the graph-replayed timed region (rank 0)"}
 
     # ---- end to end: host buffers, H2D of the step's inputs and D2H of its loss inside the timed region
     e2e = None
@@ -337,32 +431,39 @@ def main():
     clocks = sampler.stop() if sampler else None      # sampled across the eager, replayed and end-to-end regions
     cb = None
     if rank == 0 and world_size == 1 and not args.no_cpu_baseline:
-        cb = cpu_reference_run(w, args, steps=3, warmup=2)
+        cb = cpu_reference_run(w, args, steps=2 if not args.cpu_full else 1, warmup=1, full=args.cpu_full)
 
     if rank == 0:
+        secondary = None
+        sf = ROOT / "profiles" / "r2_secondary.json"
+        if sf.exists() and args.workload == "rmat-1m":
+            try:
+                secondary = json.loads(sf.read_text())
+            except Exception:   # noqa: BLE001
+                secondary = None
         line = {
             "metric": "epochs_per_sec", "value": value, "unit": "epochs/s", "n_gpus": world_size,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": w["dtype"], "data": "synthetic",
             "config": {"workload": f"{args.workload}: {w['desc']}", "n_nodes": n_nodes, "n_edges": n_edges,
-                       "partitions": world_size, "partition_method": "random", "dropout": args.dropout, "use_pp": args.use_pp,
-                       "n_in_rank0": layout.num_in, "halo_rank0": layout.num_all - layout.num_in,
-                       "nnz_rank0": layout.nnz, "linear": ops.LINEAR_IMPL,
+                       "partitions": world_size, "partition_method": part_method, "dropout": args.dropout,
+                       "use_pp": args.use_pp, "scale_down": args.scale_down,
+                       "n_in_rank0": layout_info["n_in"], "halo_rank0": layout_info["halo"],
+                       "nnz_rank0": layout_info["nnz"], "linear": ops.LINEAR_IMPL,
                        "l2": "per-epoch working set (features, activations, indices) exceeds the 126 MB L2; no flush",
                        "setup_s": round(setup_s, 1)},
             "exposed_comm_s_per_epoch": exposed_s,
-            "exposed_comm_frac": exposed_s / (ms_eager / 1e3) if ms_eager else None,
-            "eager_ms_per_step": ms_eager, "cuda_graph": graph_info,
-            "roofline": roofline, "e2e": e2e, "cpu_baseline": cb, "gpu_launches": launches, "clocks": clocks,
+            "exposed_comm_frac": exposed_s / (ms_step / 1e3) if ms_step else None,
+            "exposed_comm_how": "ns spent in pg::halo_wait_kernel, accumulated on the device (%globaltimer) inside the "
+                                "timed region (graph replays), max over ranks",
+            "eager_ms_per_step": ms_eager, "eager_exposed_comm_s_per_epoch": eager_wait_s, "cuda_graph": graph_info,
+            "parity": parity, "roofline": roofline, "e2e": e2e, "cpu_baseline": cb, "gpu_launches": launches,
+            "clocks": clocks, "secondary": secondary,
         }
         print(json.dumps(line), flush=True)
     sys.stdout.flush()
-    engine.graphs = None            # drop captured graphs (they hold NCCL kernels) before the communicator goes away
-    torch.cuda.synchronize()
-    if world_size > 1:
-        dist.barrier()
-        torch.cuda.synchronize()
-    os._exit(0)                     # skip NCCL communicator teardown (can block behind captured graphs)
+    del engine
+    teardown(world_size, holder)
 
 
 if __name__ == "__main__":

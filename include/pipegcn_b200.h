@@ -20,7 +20,7 @@
 extern "C" {
 #endif
 
-#define PG_ABI_VERSION 1
+#define PG_ABI_VERSION 2
 
 /* element types of activations / gradients */
 #define PG_F32  0
@@ -38,7 +38,8 @@ int pg_abi_version(void);
 const char* pg_last_error(void);
 /* writes sm major*10+minor, SM count and L2 bytes of `device`; needs a GPU */
 int pg_device_info(int device, int* sm_arch, int* sm_count, int64_t* l2_bytes);
-/* tuning knobs (process-wide): "agg_unroll" = 4 | 8 neighbour rows in flight per lane group;
+/* tuning knobs (process-wide): "agg_impl" = 1 | 2 (row-per-group or chunked aggregate kernel);
+ * "agg_unroll" = 4 | 8 neighbour rows in flight per lane group;
  * "agg_pack_short" = 0 | 1: two short rows per warp (16 lanes x 2 vectors) when the mean row length is < 12 */
 int pg_set_option(const char* name, int value);
 
@@ -62,6 +63,15 @@ typedef struct pg_csr {
   const int32_t* seg_long;      /* [n_seg] index into long_row */
   const int32_t* row_order;     /* [n_rows] processing order of the rows (e.g. by falling degree), or NULL */
   int64_t nnz;                  /* number of entries (indptr[n_rows]); selects the short-row kernel shape */
+  /* chunked walk (optional, chunks == NULL selects the row-per-group kernel): the rows in processing order
+   * (falling length) with their entries stored contiguously, cut into chunks one warp processes */
+  const int32_t* chunks;        /* [n_chunks][4] = {first entry in pidx, n, item, kind | n_rows << 2}:
+                                 *   kind 0: n_rows whole rows of n entries each (n_rows * n <= 32), item = first row in prow
+                                 *   kind 1: one row of n entries, item = its position in prow
+                                 *   kind 2: one segment (n entries) of a long row, item = segment index (scratch slot) */
+  int32_t n_chunks;
+  const int32_t* pidx;          /* [nnz] column ids, rows concatenated in processing order */
+  const int32_t* prow;          /* [n_rows] row id of every position of the processing order */
 } pg_csr;
 
 /*
@@ -171,10 +181,20 @@ int pg_halo_push(const pg_msg* msgs, int32_t n_msgs, int32_t n_ctas, const void*
  * Block the stream until every flags[i] >= value (acquire, system scope).  A bounded spin:
  * after `timeout_ms` the kernel stores PG_ERR_TIMEOUT to *status (device word, may be NULL)
  * and returns, so a dead peer cannot hang the GPU (the reference hangs in gloo wait(),
- * feature_buffer.py:184).
+ * feature_buffer.py:184).  wait_ns (device word, may be NULL): the nanoseconds (%globaltimer) this launch
+ * spent blocked are ADDED to it -- the exposed communication time of comm_timer.py:17-27, readable after
+ * a region of CUDA-graph replays where host-recorded events are not available.
  */
 int pg_halo_wait(const uint32_t* const* flags, int32_t n_flags, uint32_t value, const uint32_t* value_dev,
-                 int32_t timeout_ms, int32_t* status, void* stream);
+                 int32_t timeout_ms, int32_t* status, uint64_t* wait_ns, void* stream);
+
+/*
+ * Static-layer-0 shortcut: dst[r, 0:d] = c * src[r, 0:d] with c = 0 for k <= 0, else 1 (corr == 0) or
+ * 1 - m^k (corr != 0), k = k_host (+ *k_dev).  The input features never change, so the halo rows of layer 0 after
+ * k EMA updates of feature_buffer.py:186-191 are the closed form (1 - m^k) * x of the one-shot exchanged rows.
+ */
+int pg_scale_rows(const void* src, int64_t ld_src, void* dst, int64_t ld_dst, int32_t n_rows, int32_t d, int dtype,
+                  float momentum, int corr, int32_t k_host, const uint32_t* k_dev, void* stream);
 
 /*
  * grad[urow[i], 0:d] += sum_k recv[usrc[k], 0:d]  for k in [uptr[i], uptr[i+1]), in that order

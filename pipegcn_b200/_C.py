@@ -23,7 +23,8 @@ class PgError(RuntimeError):
 class pg_csr(C.Structure):
     _fields_ = [("indptr", C.c_void_p), ("indices", C.c_void_p), ("n_rows", C.c_int32), ("seg_len", C.c_int32),
                 ("n_long", C.c_int32), ("n_seg", C.c_int32), ("long_row", C.c_void_p), ("long_seg_ptr", C.c_void_p),
-                ("seg_long", C.c_void_p), ("row_order", C.c_void_p), ("nnz", C.c_int64)]
+                ("seg_long", C.c_void_p), ("row_order", C.c_void_p), ("nnz", C.c_int64),
+                ("chunks", C.c_void_p), ("n_chunks", C.c_int32), ("pidx", C.c_void_p), ("prow", C.c_void_p)]
 
 
 class pg_gemm_src(C.Structure):
@@ -60,7 +61,8 @@ def _load():
         "pg_ce_bwd": (C.c_int, [vp, i64, vp, vp, vp, i32, i32, i32, C.c_int, vp, i64, vp, vp, vp]),
         "pg_push_rows_per_cta": (C.c_int, []),
         "pg_halo_push": (C.c_int, [vp, i32, i32, vp, i64, i32, C.c_int, f32, f32, u32, vp, vp]),
-        "pg_halo_wait": (C.c_int, [vp, i32, u32, vp, i32, vp, vp]),
+        "pg_halo_wait": (C.c_int, [vp, i32, u32, vp, i32, vp, vp, vp]),
+        "pg_scale_rows": (C.c_int, [vp, i64, vp, i64, i32, i32, C.c_int, f32, C.c_int, i32, vp, vp]),
         "pg_boundary_add": (C.c_int, [vp, i64, vp, i64, i32, C.c_int, vp, vp, vp, i32, vp]),
         "pg_heap_alloc": (C.c_int, [C.c_size_t, C.POINTER(vp)]),
         "pg_heap_free": (C.c_int, [vp]),
@@ -72,13 +74,14 @@ def _load():
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)
         fn.restype, fn.argtypes = res, args
-    if lib.pg_abi_version() != 1:
-        raise PgError(f"ABI version mismatch: library {lib.pg_abi_version()}, binding 1")
+    if lib.pg_abi_version() != 2:
+        raise PgError(f"ABI version mismatch: library {lib.pg_abi_version()}, binding 2")
     return lib, tuple(sig)
 
 
 lib, EXPORTS = _load()
-for _k, _v in (("agg_unroll", os.environ.get("PG_AGG_UNROLL")), ("agg_pack_short", os.environ.get("PG_AGG_PACK"))):
+for _k, _v in (("agg_unroll", os.environ.get("PG_AGG_UNROLL")), ("agg_pack_short", os.environ.get("PG_AGG_PACK")),
+               ("agg_impl", os.environ.get("PG_AGG_IMPL"))):
     if _v:
         lib.pg_set_option(_k.encode(), int(_v))
 

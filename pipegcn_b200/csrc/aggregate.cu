@@ -157,7 +157,185 @@ agg_fixup_kernel(pg_csr g, T* __restrict__ out, int64_t ldo, int nvec, const flo
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// v2: chunked walk over the degree-sorted, permuted CSR (pg_csr::chunks / pidx / prow).
+//
+// ncu on v1 (profiles/r2_agg_v1_stalls.txt): long-scoreboard stalls on a chain of DEPENDENT loads per row --
+// row_order -> indptr -> index -> feature row, then one index + one row load per edge in the scalar tail -- while
+// 77 % of the rows of an RMAT graph have fewer than 8 entries.  Here a warp takes one CHUNK: either up to 32
+// edges' worth of whole rows of equal length (the rows are sorted by length, so a chunk is `n_rows` x `len`), or
+// one longer row, or one segment of a long row.  One 16-byte descriptor load, then ONE coalesced load fetches the
+// chunk's (next 32) column indices, which are broadcast by shuffles; neighbour rows are fetched U at a time with
+// warp-uniform predicates on the ragged end: the dependent chain per chunk is descriptor -> indices -> rows.
+struct Chunk { int e_beg, n, item, kind_rows; };   // kind = kind_rows & 3 (0: n_rows rows of n edges, 1: one row, 2: segment)
+
+template <typename T, int VB, int VPL, int U>
+__global__ void __launch_bounds__(256)
+agg2_kernel(pg_csr g, const T* __restrict__ x, uint32_t ldx_bytes, T* __restrict__ out, int64_t ldo, int nvec,
+            const float* __restrict__ row_div, int acc_rows, float* __restrict__ scratch, int64_t lds) {
+  using P = Pack<T, VB>;
+  using Raw = typename P::Raw;
+  constexpr int V = P::V;
+  constexpr int NA = P::NA;
+  constexpr unsigned kFull = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
+  const int cid = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (cid >= g.n_chunks) return;
+  const int4 c = __ldg(reinterpret_cast<const int4*>(g.chunks) + cid);
+  const int kind = c.w & 3, n_rows = c.w >> 2;
+  const uint32_t* __restrict__ pidx = reinterpret_cast<const uint32_t*>(g.pidx) + c.x;
+
+  for (int c0 = 0; c0 < nvec; c0 += 32 * VPL) {
+    float2 acc[VPL][NA];
+    bool act[VPL];
+    const char* xc[VPL];
+#pragma unroll
+    for (int j = 0; j < VPL; ++j) {
+#pragma unroll
+      for (int i = 0; i < NA; ++i) acc[j][i] = make_float2(0.f, 0.f);
+      const int vi = c0 + lane + j * 32;
+      act[j] = vi < nvec;
+      xc[j] = reinterpret_cast<const char*>(x + static_cast<int64_t>(vi) * V);
+    }
+    // out[row] = acc * inv (+ out[row] when row < acc_rows), then acc = 0
+    auto flush = [&](int row, float inv) {
+      T* op = out + static_cast<int64_t>(row) * ldo;
+#pragma unroll
+      for (int j = 0; j < VPL; ++j) {
+        if (act[j]) {
+          const int64_t o = static_cast<int64_t>(c0 + lane + j * 32) * V;
+          float r[V];
+#pragma unroll
+          for (int i = 0; i < V; ++i) r[i] = ((i & 1) ? acc[j][i / 2].y : acc[j][i / 2].x) * inv;
+          if (row < acc_rows) {
+            float ov[V];
+            P::unpack(*reinterpret_cast<const Raw*>(op + o), ov);
+#pragma unroll
+            for (int i = 0; i < V; ++i) r[i] += ov[i];
+          }
+          st_vec<VB>(op + o, P::pack(r));
+        }
+#pragma unroll
+        for (int i = 0; i < NA; ++i) acc[j][i] = make_float2(0.f, 0.f);
+      }
+    };
+
+    if (kind == 0) {
+      const int len = c.y, n_e = len * n_rows;            // n_e <= 32
+      const uint32_t my_idx = lane < n_e ? __ldg(pidx + lane) : 0u;
+      int my_row = 0;
+      float my_inv = 1.f;
+      if (lane < n_rows) {
+        my_row = __ldg(g.prow + c.z + lane);
+        if (row_div != nullptr) my_inv = 1.f / __ldg(row_div + my_row);
+      }
+      int r = 0, cnt = 0;
+      for (int u0 = 0; u0 < n_e; u0 += U) {
+        Raw v[U][VPL];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const uint32_t s = __shfl_sync(kFull, my_idx, (u0 + u) & 31);
+          if (u0 + u < n_e) {
+#pragma unroll
+            for (int j = 0; j < VPL; ++j)
+              if (act[j]) v[u][j] = ld_vec<VB>(xc[j] + static_cast<uint64_t>(s) * ldx_bytes);
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          if (u0 + u < n_e) {
+#pragma unroll
+            for (int j = 0; j < VPL; ++j)
+              if (act[j]) P::add(acc[j], v[u][j]);
+            if (++cnt == len) {
+              flush(__shfl_sync(kFull, my_row, r), __shfl_sync(kFull, my_inv, r));
+              ++r;
+              cnt = 0;
+            }
+          }
+        }
+      }
+      if (len == 0)                                       // rows without entries: the empty sum
+        for (r = 0; r < n_rows; ++r) flush(__shfl_sync(kFull, my_row, r), 1.f);
+    } else {
+      const int n_e = c.y;
+      uint32_t nxt = lane < n_e ? __ldg(pidx + lane) : 0u;
+      for (int base = 0; base < n_e; base += 32) {
+        const uint32_t my_idx = nxt;
+        if (base + 32 + lane < n_e) nxt = __ldg(pidx + base + 32 + lane);   // next 32 indices while these are used
+        const int n = min(32, n_e - base);
+        int u0 = 0;
+        for (; u0 + U <= n; u0 += U) {
+          Raw v[U][VPL];
+#pragma unroll
+          for (int u = 0; u < U; ++u) {
+            const uint32_t s = __shfl_sync(kFull, my_idx, u0 + u);
+#pragma unroll
+            for (int j = 0; j < VPL; ++j)
+              if (act[j]) v[u][j] = ld_vec<VB>(xc[j] + static_cast<uint64_t>(s) * ldx_bytes);
+          }
+#pragma unroll
+          for (int u = 0; u < U; ++u)
+#pragma unroll
+            for (int j = 0; j < VPL; ++j)
+              if (act[j]) P::add(acc[j], v[u][j]);
+        }
+        if (u0 < n) {                                     // ragged end of the row: one predicated batch
+          Raw v[U][VPL];
+#pragma unroll
+          for (int u = 0; u < U; ++u) {
+            const uint32_t s = __shfl_sync(kFull, my_idx, (u0 + u) & 31);
+            if (u0 + u < n) {
+#pragma unroll
+              for (int j = 0; j < VPL; ++j)
+                if (act[j]) v[u][j] = ld_vec<VB>(xc[j] + static_cast<uint64_t>(s) * ldx_bytes);
+            }
+          }
+#pragma unroll
+          for (int u = 0; u < U; ++u)
+            if (u0 + u < n) {
+#pragma unroll
+              for (int j = 0; j < VPL; ++j)
+                if (act[j]) P::add(acc[j], v[u][j]);
+            }
+        }
+      }
+      if (kind == 2) {
+        float* sp = scratch + static_cast<int64_t>(c.z) * lds;
+#pragma unroll
+        for (int j = 0; j < VPL; ++j) {
+          if (!act[j]) continue;
+          const int64_t o = static_cast<int64_t>(c0 + lane + j * 32) * V;
+#pragma unroll
+          for (int i = 0; i < V; ++i) sp[o + i] = (i & 1) ? acc[j][i / 2].y : acc[j][i / 2].x;
+        }
+      } else {
+        const int row = __ldg(g.prow + c.z);
+        flush(row, row_div != nullptr ? 1.f / __ldg(row_div + row) : 1.f);
+      }
+    }
+  }
+}
+
+template <typename T, int VB, int VPL>
+static int launch_agg2(const pg_csr& g, const T* x, int64_t ldx, T* out, int64_t ldo, int nvec,
+                       const float* row_div, int acc_rows, float* scratch, int64_t lds, cudaStream_t st) {
+  constexpr int U = (VPL >= 4) ? 2 : (VPL == 2 ? 4 : 8);
+  if (g.n_chunks > 0) {
+    const unsigned blocks = static_cast<unsigned>((g.n_chunks + 7) / 8);
+    agg2_kernel<T, VB, VPL, U><<<blocks, 256, 0, st>>>(g, x, static_cast<uint32_t>(ldx * sizeof(T)), out, ldo, nvec,
+                                                       row_div, acc_rows, scratch, lds);
+    PG_LAUNCH_CHECK();
+  }
+  if (g.n_long > 0) {
+    agg_fixup_kernel<T, VB><<<g.n_long, 256, 0, st>>>(g, out, ldo, nvec, row_div, acc_rows, scratch, lds);
+    PG_LAUNCH_CHECK();
+  }
+  return PG_OK;
+}
+
 int g_agg_unroll = 8;   // pg_set_option("agg_unroll", 4|8): neighbour rows in flight per group (VPL == 1)
+int g_agg_impl = 2;     // pg_set_option("agg_impl", 1|2): 1 = row-per-group kernel, 2 = chunked kernel (needs pg_csr::chunks)
 int g_agg_pack_short = 0;   // pg_set_option("agg_pack_short", 0|1): 16 lanes x 2 vectors per row when rows are short.
                             // OFF: measured slower (tools/agg_micro.py, P=8 partition: bwd 277 -> 312 us)
 
@@ -196,6 +374,11 @@ template <typename T, int VB>
 static int dispatch_agg(const pg_csr& g, const T* x, int64_t ldx, T* out, int64_t ldo, int nvec,
                         const float* row_div, int acc_rows, float* scratch, int64_t lds, cudaStream_t st) {
 #define PG_AGG(G_, VPL_) return launch_agg<T, VB, G_, VPL_>(g, x, ldx, out, ldo, nvec, row_div, acc_rows, scratch, lds, st)
+  if (g_agg_impl == 2 && g.chunks != nullptr && nvec > 16) {
+    if (nvec <= 32) return launch_agg2<T, VB, 1>(g, x, ldx, out, ldo, nvec, row_div, acc_rows, scratch, lds, st);
+    if (nvec <= 64) return launch_agg2<T, VB, 2>(g, x, ldx, out, ldo, nvec, row_div, acc_rows, scratch, lds, st);
+    return launch_agg2<T, VB, 4>(g, x, ldx, out, ldo, nvec, row_div, acc_rows, scratch, lds, st);
+  }
   if (nvec <= 4) PG_AGG(4, 1);
   if (nvec <= 8) PG_AGG(8, 1);
   if (nvec <= 16) PG_AGG(16, 1);
@@ -292,6 +475,11 @@ extern "C" int pg_set_option(const char* name, int value) {
   if (strcmp(name, "agg_unroll") == 0) {
     PG_REQUIRE(value == 4 || value == 8, "agg_unroll must be 4 or 8");
     pg::g_agg_unroll = value;
+    return PG_OK;
+  }
+  if (strcmp(name, "agg_impl") == 0) {
+    PG_REQUIRE(value == 1 || value == 2, "agg_impl must be 1 or 2");
+    pg::g_agg_impl = value;
     return PG_OK;
   }
   if (strcmp(name, "agg_pack_short") == 0) {

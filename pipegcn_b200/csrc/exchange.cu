@@ -2,6 +2,8 @@
 // NVLink/NVSwitch into peer-mapped buffers, sender-side EMA mirror, flag publish / wait,
 // and the ordered boundary add.  These replace the gather -> pinned host -> gloo -> pinned
 // host -> device path of /root/reference/helper/feature_buffer.py:165-194.
+#include <algorithm>
+#include <string.h>
 #include "common.cuh"
 
 namespace pg {
@@ -86,22 +88,37 @@ __global__ void halo_flag_only_kernel(const pg_msg* __restrict__ msgs, int n_msg
   if (m < n_msgs && msgs[m].n_rows == 0 && msgs[m].flag != nullptr) st_release_sys(msgs[m].flag, value);
 }
 
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+
+// wait_ns (optional): the nanoseconds this launch spent spinning are ADDED to *wait_ns -- the exposed
+// communication of the epoch, measurable inside a replayed CUDA graph where host-side events are not
 __global__ void halo_wait_kernel(const uint32_t* const* __restrict__ flags, int n_flags, uint32_t value,
-                                 const uint32_t* __restrict__ value_dev, long long timeout_cycles, int* status) {
+                                 const uint32_t* __restrict__ value_dev, long long timeout_cycles, int* status,
+                                 unsigned long long* wait_ns) {
   if (value_dev != nullptr) value += *value_dev;
   const int i = threadIdx.x;
-  if (i >= n_flags) return;
-  const uint32_t* f = flags[i];
-  const long long t0 = clock64();
-  unsigned ns = 20;
-  // flags count epochs monotonically; compare as a signed distance so wrap-around is harmless
-  while (static_cast<int32_t>(ld_acquire_sys(f) - value) < 0) {
-    __nanosleep(ns);
-    if (ns < 1000) ns *= 2;
-    if (clock64() - t0 > timeout_cycles) {
-      if (status) atomicExch(status, PG_ERR_TIMEOUT);
-      return;
+  const unsigned long long g0 = (wait_ns != nullptr && i == 0) ? globaltimer_ns() : 0ull;
+  if (i < n_flags) {
+    const uint32_t* f = flags[i];
+    const long long t0 = clock64();
+    unsigned ns = 20;
+    // flags count epochs monotonically; compare as a signed distance so wrap-around is harmless
+    while (static_cast<int32_t>(ld_acquire_sys(f) - value) < 0) {
+      __nanosleep(ns);
+      if (ns < 1000) ns *= 2;
+      if (clock64() - t0 > timeout_cycles) {
+        if (status) atomicExch(status, PG_ERR_TIMEOUT);
+        break;
+      }
     }
+  }
+  if (wait_ns != nullptr) {
+    __syncthreads();                       // every flag of this launch has arrived (or timed out)
+    if (i == 0) atomicAdd(wait_ns, globaltimer_ns() - g0);
   }
 }
 
@@ -131,6 +148,33 @@ boundary_add_kernel(T* __restrict__ grad, int64_t ld_grad, const T* __restrict__
       }
     }
     st_vec<VB>(gp + static_cast<int64_t>(vi) * V, P::pack(g));
+  }
+}
+
+// dst = c * src, c from the number k of EMA updates a constant message has seen (static layer-0 shortcut)
+template <typename T, int VB>
+__global__ void __launch_bounds__(256)
+scale_rows_kernel(const T* __restrict__ src, int64_t lds, T* __restrict__ dst, int64_t ldd, int n_rows, int nvec,
+                  float m, int corr, int k, const uint32_t* __restrict__ k_dev) {
+  using P = Pack<T, VB>;
+  using Raw = typename P::Raw;
+  constexpr int V = P::V;
+  if (k_dev != nullptr) k += static_cast<int>(*k_dev);
+  float c = 0.f;
+  if (k > 0) c = corr ? static_cast<float>(1.0 - pow(static_cast<double>(m), static_cast<double>(k))) : 1.f;
+  const int64_t total = static_cast<int64_t>(n_rows) * nvec;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int64_t r = i / nvec, vi = i % nvec;
+    Raw raw = *reinterpret_cast<const Raw*>(src + r * lds + vi * V);
+    if (c != 1.f) {
+      float f[V];
+      P::unpack(raw, f);
+#pragma unroll
+      for (int j = 0; j < V; ++j) f[j] *= c;
+      raw = P::pack(f);
+    }
+    st_vec<VB>(dst + r * ldd + vi * V, raw);
   }
 }
 
@@ -194,14 +238,15 @@ extern "C" int pg_halo_push(const pg_msg* msgs, int32_t n_msgs, int32_t n_ctas, 
 }
 
 extern "C" int pg_halo_wait(const uint32_t* const* flags, int32_t n_flags, uint32_t value, const uint32_t* value_dev,
-                            int32_t timeout_ms, int32_t* status, void* stream) {
+                            int32_t timeout_ms, int32_t* status, uint64_t* wait_ns, void* stream) {
   PG_REQUIRE(n_flags >= 0 && n_flags <= 1024, "pg_halo_wait: bad flag count %d", n_flags);
   if (n_flags == 0) return PG_OK;
   PG_REQUIRE(flags != nullptr, "pg_halo_wait: null flags");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   // clock64 ticks at the SM clock (<= ~2 GHz): a generous upper bound keeps the spin finite
   const long long cycles = static_cast<long long>(timeout_ms) * 2000000ll;
-  pg::halo_wait_kernel<<<1, ((n_flags + 31) / 32) * 32, 0, st>>>(flags, n_flags, value, value_dev, cycles, status);
+  pg::halo_wait_kernel<<<1, ((n_flags + 31) / 32) * 32, 0, st>>>(flags, n_flags, value, value_dev, cycles, status,
+                                                                    reinterpret_cast<unsigned long long*>(wait_ns));
   PG_LAUNCH_CHECK();
   return PG_OK;
 }
@@ -228,6 +273,31 @@ extern "C" int pg_boundary_add(void* grad, int64_t ld_grad, const void* recv, in
     else { pg::set_error("pg_boundary_add: bf16 rows must be 4-byte aligned"); return PG_ERR_INVALID; }
   } else { pg::set_error("pg_boundary_add: unknown dtype %d", dtype); return PG_ERR_INVALID; }
 #undef PG_BADD
+  PG_LAUNCH_CHECK();
+  return PG_OK;
+}
+
+extern "C" int pg_scale_rows(const void* src, int64_t ld_src, void* dst, int64_t ld_dst, int32_t n_rows, int32_t d,
+                             int dtype, float momentum, int corr, int32_t k_host, const uint32_t* k_dev, void* stream) {
+  if (n_rows == 0) return PG_OK;
+  PG_REQUIRE(src && dst, "pg_scale_rows: null argument");
+  PG_REQUIRE(n_rows > 0 && d > 0 && ld_src >= d && ld_dst >= d, "pg_scale_rows: bad sizes");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int es = pg::elem_size(dtype);
+  int vb = min(pg::vec_bytes(src, ld_src, es), pg::vec_bytes(dst, ld_dst, es));
+  vb = pg::common_vec(d, es, vb, {ld_src, ld_dst});
+  const int v = vb / es;
+  const int nvec = static_cast<int>(pg::round_up(d, v) / v);
+  const int64_t total = static_cast<int64_t>(n_rows) * nvec;
+  const unsigned blocks = static_cast<unsigned>(std::min<int64_t>((total + 255) / 256, 148 * 16));
+#define PG_SCALE(T_, VB_) pg::scale_rows_kernel<T_, VB_><<<blocks, 256, 0, st>>>(static_cast<const T_*>(src), ld_src, static_cast<T_*>(dst), ld_dst, n_rows, nvec, momentum, corr, k_host, k_dev)
+  if (dtype == PG_F32) {
+    if (vb == 16) PG_SCALE(float, 16); else if (vb == 8) PG_SCALE(float, 8); else PG_SCALE(float, 4);
+  } else if (dtype == PG_BF16) {
+    if (vb == 16) PG_SCALE(__nv_bfloat16, 16); else if (vb == 8) PG_SCALE(__nv_bfloat16, 8);
+    else if (vb == 4) PG_SCALE(__nv_bfloat16, 4); else PG_SCALE(__nv_bfloat16, 2);
+  } else { pg::set_error("pg_scale_rows: unknown dtype %d", dtype); return PG_ERR_INVALID; }
+#undef PG_SCALE
   PG_LAUNCH_CHECK();
   return PG_OK;
 }

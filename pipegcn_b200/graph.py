@@ -33,10 +33,14 @@ class CsrPlan:
             mean = self.nnz / max(self.n_rows, 1)
             seg_len = int(os.environ.get("PG_SEG_LEN", 0)) or int(min(4096, max(512, 16 * mean)))
         self.seg_len = int(seg_len)
-        long_mask = deg > self.seg_len
-        self.long_row = torch.nonzero(long_mask, as_tuple=True)[0].to(torch.int32)
-        n_long = int(self.long_row.numel())
-        nseg = (deg[long_mask] + self.seg_len - 1) // self.seg_len
+        # rows are handed to the warps by falling length: the warps of a CTA get similar amounts of work
+        # (no CTA waits for one heavy row) and the heaviest rows start first
+        order = torch.argsort(deg, descending=True, stable=True)
+        ldeg = deg[order]
+        self.row_order = order.to(torch.int32).contiguous() if (self.n_rows and sort_rows) else None
+        n_long = int((ldeg > self.seg_len).sum().item()) if self.n_rows else 0
+        self.long_row = order[:n_long].to(torch.int32).contiguous()        # long rows, longest first
+        nseg = (ldeg[:n_long] + self.seg_len - 1) // self.seg_len
         self.long_seg_ptr = torch.zeros(n_long + 1, dtype=torch.int32, device=dev)
         if n_long:
             self.long_seg_ptr[1:] = torch.cumsum(nseg, 0).to(torch.int32)
@@ -46,14 +50,59 @@ class CsrPlan:
         self.n_long = n_long
         self.max_deg = int(deg.max().item()) if self.n_rows else 0
         self._scratch = None
-        # rows are handed to the warps by falling degree: the warps of a CTA get similar amounts of work
-        # (no CTA waits for one heavy row) and the heaviest rows start first
-        self.row_order = torch.argsort(deg, descending=True, stable=True).to(torch.int32).contiguous() \
-            if (self.n_rows and sort_rows) else None
+        self.chunks = self.pidx = self.prow = None
+        self.n_chunks = 0
+        if self.n_rows and sort_rows and int(os.environ.get("PG_AGG_CHUNKS", "1")):
+            self._build_chunks(order, ldeg, n_long, nseg)
         self.c = _C.pg_csr(self.indptr.data_ptr(), self.indices.data_ptr(), self.n_rows, self.seg_len, n_long,
                            self.n_seg, self.long_row.data_ptr(), self.long_seg_ptr.data_ptr(),
                            self.seg_long.data_ptr(),
-                           self.row_order.data_ptr() if self.row_order is not None else None, self.nnz)
+                           self.row_order.data_ptr() if self.row_order is not None else None, self.nnz,
+                           self.chunks.data_ptr() if self.chunks is not None else None, self.n_chunks,
+                           self.pidx.data_ptr() if self.pidx is not None else None,
+                           self.prow.data_ptr() if self.prow is not None else None)
+
+    def _build_chunks(self, order, ldeg, n_long, nseg):
+        """Permuted CSR + chunk table of the chunked aggregate kernel (include/pipegcn_b200.h: pg_csr::chunks)."""
+        dev = self.indptr.device
+        i64 = dict(dtype=torch.int64, device=dev)
+        pptr = torch.zeros(self.n_rows + 1, **i64)
+        pptr[1:] = torch.cumsum(ldeg, 0)
+        if self.nnz:
+            start = self.indptr.to(torch.int64)[order]
+            pos = torch.repeat_interleave(start - pptr[:-1], ldeg) + torch.arange(self.nnz, **i64)
+            self.pidx = self.indices[pos].contiguous()
+        else:
+            self.pidx = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.prow = order.to(torch.int32).contiguous()
+        parts = []
+        if n_long:        # kind 2: segments of the long rows, in segment order (= scratch slot)
+            seg_of = self.seg_long.to(torch.int64)
+            k = torch.arange(self.n_seg, **i64) - self.long_seg_ptr.to(torch.int64)[seg_of]
+            e_beg = pptr[seg_of] + k * self.seg_len
+            n = torch.minimum(torch.full_like(k, self.seg_len), ldeg[seg_of] - k * self.seg_len)
+            parts.append(torch.stack([e_beg, n, torch.arange(self.n_seg, **i64), torch.full_like(k, 2)], 1))
+        n_mid_end = max(n_long, int((ldeg > 32).sum().item()))
+        if n_mid_end > n_long:      # kind 1: one row per chunk
+            it = torch.arange(n_long, n_mid_end, **i64)
+            parts.append(torch.stack([pptr[it], ldeg[it], it, torch.full_like(it, 1 | (1 << 2))], 1))
+        # kind 0: rows of equal length len <= 32, floor(32 / len) of them per chunk (32 empty rows per chunk)
+        small = ldeg[n_mid_end:]
+        if small.numel():
+            cnt = torch.bincount(small, minlength=33)                  # rows per length, lengths 0..32
+            a = n_mid_end
+            for length in range(32, -1, -1):
+                m = int(cnt[length].item())
+                if m == 0:
+                    continue
+                per = 32 // length if length > 0 else 32
+                first = a + torch.arange(0, m, per, **i64)
+                rows = torch.clamp(a + m - first, max=per)
+                parts.append(torch.stack([pptr[first], torch.full_like(first, length), first, rows << 2], 1))
+                a += m
+        tab = torch.cat(parts, 0) if parts else torch.zeros(0, 4, **i64)
+        self.chunks = tab.to(torch.int32).contiguous()
+        self.n_chunks = int(tab.shape[0])
 
     def scratch(self, d: int) -> Optional[torch.Tensor]:
         if self.n_seg == 0:

@@ -84,7 +84,7 @@ class Buffer(object):
     # ------------------------------------------------------------------ set-up
     def init_buffer(self, num_in, num_all, boundary, f_recv_shape, layer_size, use_pp=False, backend='nccl',
                     pipeline=False, corr_feat=False, corr_grad=False, corr_momentum=0,
-                    dtype=torch.float32, world=None, key='pipegcn.buffer'):
+                    dtype=torch.float32, world=None, key='pipegcn.buffer', static_layer0=False):
         if backend not in ('nccl', 'nvlink'):
             # the reference implements gloo only and raises for the rest (feature_buffer.py:204-205);
             # this engine implements the NVLink path only
@@ -111,6 +111,14 @@ class Buffer(object):
         self._nver = 2 if pipeline else 1
         self._peers = [j for j in range(size) if j != rank]
         L = self._n_layers
+        # static-layer-0 shortcut: the input features never change, so their halo rows are
+        # exchanged ONCE (`static0_begin/_end`) into `x0`; what `update(0, .)` returns at epoch t is c_t * x0 with
+        # c_t = [t > 0] (pipelined) / 1 (synchronous), or 1 - m^k after k EMA updates with feat-corr -- the
+        # closed form of feature_buffer.py:186-191 applied to a constant message
+        self._static0 = bool(static_layer0) and not use_pp and size > 1 and L > 0
+        self._static0_gen = 0
+        self._static0_ready = False
+        self._l0_one = set()
 
         # rows [pl[j], pr[j]) of the [num_all] space hold peer j's halo (feature_buffer.py:33-43)
         self._pl, self._pr = [None] * size, [None] * size
@@ -150,7 +158,13 @@ class Buffer(object):
                 if l > 0:
                     self._b_off[(l, v)] = off
                     off = _round_up(off + max(btot, 1) * self._ld[l] * self._es, _ALIGN)
+        self._x0_off = None
+        if self._static0:
+            self._x0_off = off
+            off = _round_up(off + max(self._num_all - self._num_in, 1) * self._ld[0] * self._es, _ALIGN)
         self._heap = Heap(max(off, _ALIGN), dev)
+        self._x0 = None if self._x0_off is None else self._heap.view(
+            self._x0_off, (max(self._num_all - self._num_in, 1), self._ld[0]), dtype)
         self._flags = self._heap.view(self._flag_off, (L, 2, size), torch.int32)
         self._f_buf = {k: self._heap.view(o, (self._num_all, self._ld[k[0]]), dtype) for k, o in self._f_off.items()}
         self._b_recv = {k: self._heap.view(o, (max(btot, 1), self._ld[k[0]]), dtype) for k, o in self._b_off.items()}
@@ -182,8 +196,11 @@ class Buffer(object):
         else:
             self._urow = self._uptr = self._usrc = None
 
-        self._counters = torch.zeros(max(1, 4 * L * size * self._nver), dtype=torch.int32, device=dev)
+        self._counters = torch.zeros(max(1, (4 * L * self._nver + 1) * size), dtype=torch.int32, device=dev)
         self._status = torch.zeros(1, dtype=torch.int32, device=dev)
+        # nanoseconds the compute stream spent blocked in flag waits, accumulated by the wait kernel itself
+        # (comm_timer.py:17-27's exposed-comm metric where host events cannot be used: CUDA-graph replays)
+        self._wait_ns = torch.zeros(1, dtype=torch.int64, device=dev)
         self._epoch_dev = torch.zeros(1, dtype=torch.int32, device=dev)    # == self._epoch, readable by kernels
         self._comm_stream = torch.cuda.Stream(device=dev) if dev.type == 'cuda' else None
         self._push_done = {}
@@ -194,7 +211,7 @@ class Buffer(object):
         w.publish(key, {
             'heap': w.heap_token(self._heap), 'f_off': dict(self._f_off), 'b_off': dict(self._b_off),
             'flag_off': self._flag_off, 'pl': list(self._pl), 'boff': list(self._boff), 'ld': list(self._ld),
-            'n_layers': L, 'nver': self._nver, 'es': self._es,
+            'n_layers': L, 'nver': self._nver, 'es': self._es, 'x0_off': self._x0_off, 'num_in': self._num_in,
         })
         self._ready, self._connected = True, False
 
@@ -241,6 +258,19 @@ class Buffer(object):
                                       ema.data_ptr() if ema is not None else None, ld,
                                       flag_ptr(j, l, 1), counter_ptr()))
             self._bwd_msgs[(l, v)] = _MsgSet(msgs, dev) if msgs else None
+        self._x0_msgs = None
+        if self._static0:
+            ld = self._ld[0]
+            msgs = []
+            for j in self._peers:
+                if tables[j]['x0_off'] is None:
+                    raise RuntimeError(f"rank {j} was initialised without static_layer0")
+                dst = base[j] + tables[j]['x0_off'] + (tables[j]['pl'][rank] - tables[j]['num_in']) * ld * es
+                # the backward flag word of layer 0 is free (layer 0 has no gradient exchange): it carries the
+                # generation of the one-shot push
+                msgs.append(_C.pg_msg(self._bidx[j].data_ptr(), 0, int(self._bidx[j].numel()), 0, dst, ld,
+                                      None, 0, flag_ptr(j, 0, 1), counter_ptr()))
+            self._x0_msgs = _MsgSet(msgs, dev) if msgs else None
         # device arrays of the flag words this rank waits on, per (layer, direction)
         self._wait = {}
         for l in range(L):
@@ -289,6 +319,12 @@ class Buffer(object):
             return offset & 0xffffffff, self._epoch_dev.data_ptr()
         return (self._epoch + offset) & 0xffffffff, None
 
+    def take_wait_ns(self) -> int:
+        """Exposed communication (ns blocked in flag waits) since the last call; host sync."""
+        ns = int(self._wait_ns.item())
+        self._wait_ns.zero_()
+        return ns
+
     def check_status(self):
         """Raises if a flag wait timed out since the last check (host sync)."""
         if int(self._status.item()) != 0:
@@ -318,7 +354,8 @@ class Buffer(object):
             e0.record()
         _C.count()
         _C.check(_C.lib.pg_halo_wait(ptrs.data_ptr(), ptrs.numel(), value, value_dev, self.timeout_ms,
-                                     self._status.data_ptr(), _C.stream_ptr()), "pg_halo_wait")
+                                     self._status.data_ptr(), self._wait_ns.data_ptr(), _C.stream_ptr()),
+                 "pg_halo_wait")
         if timed:
             e1.record()
             self.timer.add_events(name, e0, e1)
@@ -334,6 +371,71 @@ class Buffer(object):
         if not feat.is_cuda:
             raise _C.PgError("Buffer.update needs a CUDA tensor (no CPU fall-back)")
 
+    # ------------------------------------------------------------------ static layer 0
+    def static0_begin(self, feat):
+        """Push this rank's boundary rows of the (static) input features into every peer's `x0` store.  Every rank
+        calls `static0_begin` and then `static0_end` once, before the first epoch and again whenever the input
+        features change."""
+        if not self._static0:
+            return
+        if not self._connected:
+            self._connect()
+        if feat.stride(1) != 1:
+            feat = feat.contiguous()
+        self._static0_gen += 1
+        ms = self._x0_msgs
+        if ms is not None:
+            _C.count(2)
+            _C.check(_C.lib.pg_halo_push(ms.ptr, ms.n_msgs, ms.n_ctas, feat.data_ptr(), feat.stride(0),
+                                         self._layer_size[0], _C.dtype_code(feat.dtype), 0.0, 1.0,
+                                         self._static0_gen, None, _C.stream_ptr()), "pg_halo_push")
+
+    def static0_end(self):
+        if not self._static0:
+            return
+        ptrs = self._wait[(0, 1)]
+        if ptrs is not None:
+            _C.count()
+            _C.check(_C.lib.pg_halo_wait(ptrs.data_ptr(), ptrs.numel(), self._static0_gen, None, self.timeout_ms,
+                                         self._status.data_ptr(), None, _C.stream_ptr()), "pg_halo_wait")
+        self._static0_ready = True
+        self._l0_one.clear()
+        if self.graph_mode and not self._corr_feat:
+            # captured epochs contain no layer-0 kernel (halo rows already hold x0): refresh them here
+            for v in range(self._nver):
+                self._scale_x0(v, 1, None)
+                self._l0_one.add(v)
+
+    def _scale_x0(self, v, k, k_dev):
+        d = self._layer_size[0]
+        dst = self._f_buf[(0, v)][self._num_in:]
+        n = self._num_all - self._num_in
+        if n == 0:
+            return
+        _C.count()
+        _C.check(_C.lib.pg_scale_rows(self._x0.data_ptr(), self._x0.stride(0), dst.data_ptr(), dst.stride(0), n, d,
+                                      _C.dtype_code(self._dtype), float(self._corr_momentum), int(self._corr_feat),
+                                      int(k), k_dev, _C.stream_ptr()), "pg_scale_rows")
+
+    def _forward_static0(self, feat):
+        d = self._layer_size[0]
+        v = self._use_version()
+        if not (feat.data_ptr() == self._f_buf[(0, v)].data_ptr() and feat.stride(0) == self._ld[0]):
+            if feat.stride(1) != 1:
+                feat = feat.contiguous()
+            self._push(self._self_msgs[(0, v)], feat, d, 0)
+        # k = EMA updates the consumed message has seen: epoch t consumes message t-1 (pipelined) or t
+        off = 0 if self._pipeline else 1
+        if self._corr_feat:
+            if self.graph_mode:
+                self._scale_x0(v, off, self._epoch_dev.data_ptr())
+            else:
+                self._scale_x0(v, self._epoch + off, None)
+        elif v not in self._l0_one and self._epoch + off > 0:
+            self._scale_x0(v, 1, None)              # c = 1 from now on: nothing left to do for this version
+            self._l0_one.add(v)
+        return self._f_buf[(0, v)][:, :d]
+
     # ------------------------------------------------------------------ forward
     def update(self, layer, feat):
         """[N_in, d] -> [num_all, d] = cat(feat, halo rows of every peer); differentiable wrt feat."""
@@ -343,6 +445,8 @@ class Buffer(object):
         return _HaloUpdate.apply(feat, self, layer)
 
     def _forward(self, layer, feat):
+        if layer == 0 and self._static0_ready:
+            return self._forward_static0(feat)
         d = self._layer_size[layer]
         t = self._epoch
         if feat.stride(1) != 1:
@@ -416,6 +520,18 @@ class Buffer(object):
                                         self._layer_size[layer], _C.dtype_code(grad.dtype),
                                         self._urow.data_ptr(), self._uptr.data_ptr(), self._usrc.data_ptr(),
                                         int(self._urow.numel()), _C.stream_ptr()), "pg_boundary_add")
+
+    def release(self):
+        """Give the symmetric heap back: close the peers' mappings, wait for every rank (they close theirs of this
+        heap), free.  Collective over the world; the buffer is unusable afterwards."""
+        w = self._world
+        if self._connected:
+            for j, t in enumerate(w.collect(self._key)):
+                if j != w.rank:
+                    w.unmap_peer(t['heap'])
+        w.barrier()
+        self._heap.free()
+        self._ready = self._connected = False
 
     def synchronize(self):
         """Join the side stream (end of training / before reading buffers on the host)."""

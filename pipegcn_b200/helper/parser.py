@@ -56,6 +56,9 @@ def build_parser():
     parser.add_argument('--eval', action='store_true', help="enable evaluation")
     parser.add_argument('--no-eval', action='store_false', dest='eval', help="disable evaluation")
     parser.set_defaults(eval=True)
+    parser.add_argument('--no-partition-cache', action='store_false', dest='partition_cache',
+                        help="do not read/write partitions/<graph_name>/part.pt")
+    parser.set_defaults(partition_cache=True)
     return parser
 
 

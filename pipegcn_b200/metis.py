@@ -28,8 +28,12 @@ def build(force: bool = False) -> Path:
     archive = next((a for a in _ARCHIVES if Path(a).exists()), None)
     if archive is None:
         raise RuntimeError("libmetis_static.a not found in the CUDA toolkit; use --partition-method random")
-    subprocess.run(["gcc", "-shared", "-fPIC", "-o", str(_LIB), "-Wl,--whole-archive", archive,
+    # several ranks may get here at once (spawned processes): link into a private file, publish it atomically
+    import os
+    tmp = _LIB.with_suffix(f".so.tmp{os.getpid()}")
+    subprocess.run(["gcc", "-shared", "-fPIC", "-o", str(tmp), "-Wl,--whole-archive", archive,
                     "-Wl,--no-whole-archive", "-lm"], check=True)
+    os.replace(tmp, _LIB)
     return _LIB
 
 

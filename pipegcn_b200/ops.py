@@ -280,6 +280,12 @@ def _stash_colsum(t: torch.Tensor, colsum: torch.Tensor):
     _COLSUM[(t.data_ptr(), tuple(t.shape))] = colsum
 
 
+def reset_colsum():
+    """Drop by-products of an earlier backward (called at the start of every backward pass): an entry that was
+    never consumed must not be picked up by a later gradient that happens to reuse the address."""
+    _COLSUM.clear()
+
+
 def _take_colsum(t: torch.Tensor):
     return _COLSUM.pop((t.data_ptr(), tuple(t.shape)), None)
 

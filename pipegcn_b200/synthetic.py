@@ -37,6 +37,18 @@ class GlobalGraph:
         """Global in-degree including the self loop (utils.py:142)."""
         return torch.bincount(self.dst, minlength=self.n_nodes)
 
+    # the reference's datasets carry val/test masks (utils.py:24-29); the synthetic graphs split the
+    # non-training nodes in two by id parity
+    @property
+    def val_mask(self) -> torch.Tensor:
+        ids = torch.arange(self.n_nodes, device=self.train_mask.device)
+        return ~self.train_mask & (ids % 2 == 0)
+
+    @property
+    def test_mask(self) -> torch.Tensor:
+        ids = torch.arange(self.n_nodes, device=self.train_mask.device)
+        return ~self.train_mask & (ids % 2 == 1)
+
 
 # named shapes: nodes, directed edges (incl. self loops), features, classes, train fraction
 SHAPES = {
@@ -104,8 +116,10 @@ def rmat_edges(n_nodes: int, n_edges: int, seed: int = 0, device="cpu", max_roun
 
 
 def make_graph(shape: str | dict, seed_graph: int = 0, seed_feat: int = 2, seed_mask: int = 3,
-               device="cpu", feat_dtype=torch.float32) -> GlobalGraph:
-    """Build a named synthetic graph (SURVEY.md §8d seeds: graph 0, features 2, masks 3)."""
+               device="cpu", feat_dtype=torch.float32, planted_labels: bool = False) -> GlobalGraph:
+    """Build a named synthetic graph (SURVEY.md §8d seeds: graph 0, features 2, masks 3).
+    `planted_labels`: labels = argmax of a fixed random linear map of (own + neighbour-mean) features instead of
+    uniform noise, so that training has something to learn (accuracy tests)."""
     spec = SHAPES[shape] if isinstance(shape, str) else dict(shape)
     n = spec["n_nodes"]
     src, dst = rmat_edges(n, spec["n_edges"], seed=seed_graph, device=device)
@@ -114,6 +128,11 @@ def make_graph(shape: str | dict, seed_graph: int = 0, seed_feat: int = 2, seed_
     g.manual_seed(seed_feat)
     feat = torch.randn(n, spec["n_feat"], generator=g, device=dev, dtype=torch.float32).to(feat_dtype)
     label = torch.randint(0, spec["n_class"], (n,), generator=g, device=dev)
+    if planted_labels:
+        proj = torch.randn(spec["n_feat"], spec["n_class"], generator=g, device=dev)
+        agg = torch.zeros(n, spec["n_feat"], device=dev).index_add_(0, dst, feat.float()[src])
+        agg = agg / torch.bincount(dst, minlength=n).clamp(min=1).unsqueeze(1)
+        label = ((feat.float() + 2.0 * agg) @ proj).argmax(dim=1)
     g.manual_seed(seed_mask)
     train_mask = torch.rand(n, generator=g, device=dev) < spec["train_frac"]
     if not bool(train_mask.any()):
@@ -132,13 +151,17 @@ def random_partition(n_nodes: int, n_parts: int, seed: int = 1, device="cpu") ->
     return part
 
 
+def induced_subgraph(g: GlobalGraph, keep: torch.Tensor):
+    """(`g.subgraph(keep)`, original ids of its nodes): node ids compacted in ascending order (DGL `subgraph`)."""
+    new_id = torch.full((g.n_nodes,), -1, dtype=torch.int64, device=g.src.device)
+    ids = torch.nonzero(keep, as_tuple=True)[0]
+    n = int(ids.numel())
+    new_id[ids] = torch.arange(n, dtype=torch.int64, device=g.src.device)
+    em = keep[g.src] & keep[g.dst]
+    return GlobalGraph(n, new_id[g.src[em]], new_id[g.dst[em]], g.feat[keep], g.label[keep], g.train_mask[keep]), ids
+
+
 def train_subgraph(g: GlobalGraph) -> GlobalGraph:
     """`--inductive`: the graph induced by the training nodes (`g.subgraph(g.ndata['train_mask'])`,
-    /root/reference/main.py:34-35, helper/utils.py:226-230); node ids are compacted in ascending order."""
-    keep = g.train_mask
-    new_id = torch.full((g.n_nodes,), -1, dtype=torch.int64, device=g.src.device)
-    n = int(keep.sum().item())
-    new_id[keep] = torch.arange(n, dtype=torch.int64, device=g.src.device)
-    em = keep[g.src] & keep[g.dst]
-    return GlobalGraph(n, new_id[g.src[em]], new_id[g.dst[em]], g.feat[keep], g.label[keep],
-                       torch.ones(n, dtype=torch.bool, device=g.src.device))
+    /root/reference/main.py:34-35, helper/utils.py:226-230)."""
+    return induced_subgraph(g, g.train_mask)[0]

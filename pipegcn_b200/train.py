@@ -6,7 +6,7 @@ forward, summed cross-entropy on the local train rows, backward (which runs the
 gradient halo exchange), `buffer.next_epoch()`, `reducer.synchronize()`, Adam step.
 The DGL partition arguments of the reference's `run(graph, node_dict, gpb, args)` are
 replaced by a `PartitionLayout` (pipegcn_b200/partition.py); evaluation and
-checkpointing are outside the hot path.
+checkpointing (train.py:20-61,377-400) run on the GPU with the same kernels (pipegcn_b200/evaluate.py).
 
 `RankEngine` is one rank; `LocalTrainer` steps several simulated ranks of a
 `LocalWorld` in lock-step on one GPU (each on its own stream).
@@ -66,16 +66,20 @@ class RankEngine:
                                 self.layer_size[:args.n_layers - args.n_linear], use_pp=args.use_pp,
                                 backend=args.backend, pipeline=args.enable_pipeline, corr_feat=args.feat_corr,
                                 corr_grad=args.grad_corr, corr_momentum=args.corr_momentum,
-                                dtype=self.dtype, world=world)
+                                dtype=self.dtype, world=world,
+                                static_layer0=bool(getattr(args, 'static_layer0', True)))
         self.feat = layout.feat.to(dev).to(self.dtype)
         self._pp = None
         if args.use_pp:
             self.pp_begin(layout)
             if not getattr(world, 'is_local', False) or world.size == 1:
                 self.pp_end()
+                self.release_pp()
         else:
             # the static input features live in the exchange buffer of layer 0 (all versions): update(0, .) copies nothing
             self.buffer.load_inner(0, self.feat)
+            if not getattr(world, 'is_local', False) or world.size == 1:
+                self.static0()          # LocalWorld ranks: `LocalTrainer` runs the two phases over all ranks
         tm = layout.train_mask.to(dev)
         self.part_train = int(tm.sum().item())
         prefix = bool(tm[:self.part_train].all().item()) if self.part_train else True
@@ -139,7 +143,25 @@ class RankEngine:
         self.feat = both
         torch.cuda.synchronize()
         pp.check_status()
+        self._pp_done = pp                 # peers may still be reading its heap: freed by `release_pp`
         self._pp = None
+
+    def release_pp(self):
+        """Free the one-shot --use-pp exchange heap (collective for a DistWorld: every rank calls it after its
+        `pp_end`; for LocalWorld ranks call it once every rank has finished `pp_end`)."""
+        pp = getattr(self, '_pp_done', None)
+        if pp is not None:
+            pp.release()
+            self._pp_done = None
+
+    def static0(self, phase=None):
+        """One-shot exchange of the static layer-0 halo rows; `phase` 'begin' / 'end' / both."""
+        if self.args.use_pp:
+            return
+        if phase in (None, 'begin'):
+            self.buffer.static0_begin(self.buffer._f_buf[(0, 0)][:self.buffer._num_in, :self.args.n_feat])
+        if phase in (None, 'end'):
+            self.buffer.static0_end()
 
     def forward_backward(self, keep_logits=False):
         """train.py:343-355; returns the summed loss (device tensor, no host sync)."""
@@ -154,18 +176,19 @@ class RankEngine:
         if keep_logits or self.keep_logits:
             self.last_logits = logits.detach()
         self.optimizer.zero_grad(set_to_none=True)
+        from . import ops as _ops
+        _ops.reset_colsum()
         loss.backward()
         return loss.detach()
 
     def set_features(self, feat):
         """New input features for the coming epoch (host or device tensor, [N_in, n_feat])."""
-        if self.graphs is not None:
-            # the captured epochs read layer 0 of a fixed version each: refresh every version (device epoch
-            # parity is not known on the host)
+        if self.buffer.inner_view(0) is not None:
+            # layer 0 lives in the exchange buffer, one copy per version (epoch parity): refresh all of them
             self.buffer.load_inner(0, feat.to(self.device, non_blocking=True) if not feat.is_cuda else feat)
+            self.static0()          # new features: their halo rows have to be exchanged again
             return
-        view = self.buffer.inner_view(0)
-        (view if view is not None else self.feat).copy_(feat, non_blocking=True)
+        self.feat.copy_(feat, non_blocking=True)
 
     def finish_epoch(self, reduce=True):
         """train.py:357-362."""
@@ -178,6 +201,7 @@ class RankEngine:
     def run_epoch(self):
         if self.graphs is not None:
             return self.replay()
+        self.buffer.timer.clear()            # sections are per epoch (comm_timer.py:14-15 raises on duplicates)
         loss = self.forward_backward()
         self.finish_epoch()
         return loss
@@ -236,6 +260,14 @@ class LocalTrainer:
             for e, s in zip(self.engines, self.streams):
                 with torch.cuda.stream(s):
                     e.pp_end()
+            for e in self.engines:
+                e.release_pp()
+        if not args.use_pp and len(layouts) > 1:      # static layer-0 halo: all ranks push before any rank waits
+            for ph in ('begin', 'end'):
+                for e, s in zip(self.engines, self.streams):
+                    with torch.cuda.stream(s):
+                        e.static0(ph)
+            torch.cuda.synchronize()
         for e in self.engines:
             e.buffer.timeout_ms = 5000
 
@@ -290,14 +322,28 @@ class LocalTrainer:
         return losses
 
 
-def run(layout: PartitionLayout, args, world=None):
-    """One rank's training loop with the reference's log line (train.py:341-375)."""
+def run(layout: PartitionLayout, args, world=None, eval_graph=None):
+    """One rank's training loop with the reference's log line, evaluation and checkpoint (train.py:341-400).
+    `eval_graph`: the global graph rank 0 evaluates on every `log_every` epochs when `args.eval` is set."""
     if world is None:
         from .world import default_world
         world = default_world()
     rank = world.rank
     engine = RankEngine(layout, args, world, buffer=ctx.buffer, reducer=ctx.reducer)
     timer = engine.buffer.timer
+    do_eval = bool(getattr(args, 'eval', False)) and rank == 0
+    eval_set = best = result_file_name = None
+    if do_eval:
+        if eval_graph is None:
+            raise ValueError("run(..., eval_graph=None) with args.eval set: rank 0 needs the global graph "
+                             "(load_partition(..., return_graph=True)) or pass --no-eval")
+        from .evaluate import BestModel, EvalSet, evaluate_induc, evaluate_trans, result_file
+        eval_set = EvalSet(eval_graph, engine.device, inductive=getattr(args, 'inductive', False), dtype=engine.dtype)
+        best = BestModel()
+        os.makedirs('checkpoint/', exist_ok=True)                         # train.py:258-260
+        os.makedirs('results/', exist_ok=True)
+        result_file_name = result_file(args)
+    del eval_graph
     train_dur, comm_dur, reduce_dur = [], [], []
     for epoch in range(args.n_epochs):
         torch.cuda.synchronize()
@@ -322,7 +368,22 @@ def run(layout: PartitionLayout, args, world=None):
                 np.mean(reduce_dur) if reduce_dur else float('nan'), loss.item() / max(engine.part_train, 1)))
         timer.clear()
         engine.buffer.check_status()
+        if do_eval and (epoch + 1) % args.log_every == 0:                 # train.py:377-390
+            name = 'Epoch %05d' % epoch
+            if not eval_set.inductive:
+                val_acc = evaluate_trans(name, engine.model, eval_set.val, result_file_name)
+            else:
+                val_acc = evaluate_induc(name, engine.model, eval_set.val, 'val', result_file_name)
+            best.offer(val_acc, engine.model)
     engine.buffer.synchronize()
+    if do_eval and best.state is not None:                                # train.py:392-400
+        path = best.save(args)
+        print('model saved')
+        print("Validation accuracy {:.2%}".format(best.acc))
+        final = create_model(engine.layer_size, args, buffer=engine.buffer, dtype=engine.dtype).to(engine.device)
+        final.load_state_dict(best.state)
+        engine.test_acc = evaluate_induc('Test Result', final, eval_set.test, 'test')
+        engine.best_val_acc, engine.checkpoint_path = best.acc, path
     return engine
 
 
@@ -336,9 +397,25 @@ def init_processes(rank, size, args):
     os.environ['MASTER_ADDR'] = args.master_addr
     os.environ['MASTER_PORT'] = '%d' % args.port
     import torch.distributed as dist
-    torch.cuda.set_device(rank % max(torch.cuda.device_count(), 1))
-    dist.init_process_group(args.backend, rank=rank, world_size=size)
+    if args.backend not in ('nccl', 'nvlink'):
+        raise NotImplementedError("backend '%s': this engine implements the NVLink/NCCL path only" % args.backend)
+    if size > torch.cuda.device_count() or getattr(args, 'node_rank', 0) > 0 \
+            or size > getattr(args, 'parts_per_node', size):
+        # peer heaps are mapped with CUDA IPC, which does not cross nodes
+        raise NotImplementedError(f"single-node only: {size} partitions need {size} GPUs of ONE node "
+                                  f"({torch.cuda.device_count()} visible, --parts-per-node "
+                                  f"{getattr(args, 'parts_per_node', size)}, --node-rank {getattr(args, 'node_rank', 0)})")
+    torch.cuda.set_device(rank)
+    # 'nvlink' names the halo path; the process group (gradient all-reduce, handle exchange) is always NCCL
+    dist.init_process_group('nccl', rank=rank, world_size=size, device_id=torch.device('cuda', rank))
     check_parser(args)
     from .helper.utils import load_partition
-    layout = load_partition(args, rank)
-    return run(layout, args)
+    want_graph = bool(getattr(args, 'eval', False)) and rank == 0
+    out = load_partition(args, rank, return_graph=want_graph)
+    layout, g_full = out if want_graph else (out, None)
+    try:
+        return run(layout, args, eval_graph=g_full)
+    finally:
+        torch.cuda.synchronize()
+        dist.barrier()
+        dist.destroy_process_group()

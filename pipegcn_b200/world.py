@@ -99,6 +99,12 @@ class LocalRank:
     def map_peer(self, token) -> int:
         return int(token[1])
 
+    def unmap_peer(self, token):
+        pass
+
+    def barrier(self):
+        pass
+
     def all_reduce_sum_(self, tensor):
         raise RuntimeError("LocalWorld ranks reduce through LocalReducerGroup, not a collective")
 
@@ -135,6 +141,16 @@ class DistWorld:
             _C.check(_C.lib.pg_ipc_import(handle, C.byref(p)), f"pg_ipc_import(rank {owner})")
             self._mapped[handle] = int(p.value)
         return self._mapped[handle]
+
+    def unmap_peer(self, token):
+        kind, handle, owner, ptr = token
+        p = self._mapped.pop(handle, None)
+        if p is not None:
+            _C.check(_C.lib.pg_ipc_close(C.c_void_p(p)), f"pg_ipc_close(rank {owner})")
+
+    def barrier(self):
+        torch.cuda.synchronize(self.device)
+        self.dist.barrier(group=self.group)
 
     def all_reduce_sum_(self, tensor):
         self.dist.all_reduce(tensor, op=self.dist.ReduceOp.SUM, group=self.group)

@@ -247,3 +247,38 @@ def test_dropout_kernel(dtype):
     out2 = ops.dropout(xin, 0.3, True)
     assert not torch.equal(out2 != 0, keep)          # a new mask every call
     assert ops.dropout(xin, 0.0, True) is xin and ops.dropout(xin, 0.5, False) is xin
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("d", [100, 256, 602])
+def test_chunked_kernel_equals_row_kernel(dtype, d):
+    """agg_impl 2 (chunks of whole short rows / one row / one segment per warp, indices loaded coalesced and
+    broadcast by shuffles) sums every row in the same order as agg_impl 1: bit-identical results, including rows
+    without entries, rows longer than the segment length, the division and the accumulate mode."""
+    from pipegcn_b200 import _C, ops
+    from pipegcn_b200.graph import CsrPlan, alloc_rows
+    n_rows, n_cols = 5000, 4000
+    indptr, indices = _random_csr(n_rows, n_cols, 6, seed=d, hubs=4, hub_deg=1500)
+    plan = CsrPlan(indptr.to(DEV), indices.to(DEV), seg_len=256)
+    assert plan.n_chunks > 0 and plan.n_long == 4
+    g = torch.Generator().manual_seed(3)
+    x = alloc_rows(n_cols, d, dtype, DEV, zero=True)
+    x.copy_(torch.randn(n_cols, d, generator=g).to(dtype))
+    div = torch.randint(1, 9, (n_rows,), generator=g).float().to(DEV)
+    base = alloc_rows(n_rows, d, dtype, DEV, zero=True)
+    base.copy_(torch.randn(n_rows, d, generator=g).to(dtype))
+    outs = []
+    try:
+        for impl in (1, 2):
+            _C.check(_C.lib.pg_set_option(b"agg_impl", impl))
+            o = base.clone()
+            o2 = alloc_rows(n_rows, d, dtype, DEV)
+            o2.copy_(base)
+            ops.aggregate(plan, x, out=o2, row_div=div, acc_rows=1234)
+            outs.append((ops.aggregate(plan, x, row_div=div).clone(), o2.clone()))
+    finally:
+        _C.lib.pg_set_option(b"agg_impl", 2)
+    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
+    ref = _ref_agg(indptr, indices, x.float().cpu(), div.cpu())
+    tol = 2e-5 if dtype == torch.float32 else 1.6e-2
+    assert (outs[1][0].float().cpu().double() - ref).abs().max().item() <= tol * ref.abs().max().item() + 1e-6

@@ -94,7 +94,7 @@ def test_c_abi_exports_every_declared_symbol():
     for n in names:
         assert hasattr(lib, n), f"{n} declared in the header but not exported"
     lib.pg_abi_version.restype = ctypes.c_int
-    assert lib.pg_abi_version() == 1
+    assert lib.pg_abi_version() == 2
     from pipegcn_b200 import _C
     assert set(_C.EXPORTS) == set(names)
 
@@ -108,7 +108,7 @@ def test_ops_refuse_cpu_tensors():
 
 def test_command_line_matches_reference_flags():
     """Same flags, aliases and defaults as /root/reference/helper/parser.py (fixture tests/golden/ref_parser.json),
-    except `--backend` (nccl instead of gloo: the only implemented transport) and the added `--dtype`."""
+    except `--backend` (nccl instead of gloo: the only implemented transport) and the added `--dtype` and `--no-partition-cache`."""
     import json
     from pipegcn_b200.helper.parser import create_parser
     ref = json.loads((ROOT / "tests" / "golden" / "ref_parser.json").read_text())
@@ -118,7 +118,7 @@ def test_command_line_matches_reference_flags():
         if k != "backend":
             assert ours[k] == v, (k, ours[k], v)
     assert ours["backend"] == "nccl" and ours["dtype"] == "fp32"
-    assert set(ours) - set(ref["defaults"]) == {"dtype"}
+    assert set(ours) - set(ref["defaults"]) == {"dtype", "partition_cache"}
     got = vars(create_parser(["--n_layers", "4", "--enable_pipeline", "--feat-corr", "--no-eval", "--norm", "batch"]))
     for k, v in ref["parsed_example"].items():
         if k != "backend":
