@@ -431,7 +431,9 @@ def main():
     clocks = sampler.stop() if sampler else None      # sampled across the eager, replayed and end-to-end regions
     cb = None
     if rank == 0 and world_size == 1 and not args.no_cpu_baseline:
-        cb = cpu_reference_run(w, args, steps=2 if not args.cpu_full else 1, warmup=1, full=args.cpu_full)
+        # same graph as the GPU arm when one CPU epoch takes ~20 s (<= 25 M edges), else the stated 1/16 sample
+        cpu_full = args.cpu_full or n_edges <= 25_000_000
+        cb = cpu_reference_run(w, args, steps=1 if cpu_full else 2, warmup=1, full=cpu_full)
 
     if rank == 0:
         secondary = None

@@ -114,6 +114,18 @@ typedef struct pg_gemm_src {
 int pg_linear(int dtype_in, int dtype_out, const pg_gemm_src* srcs, int32_t n_src, const float* bias,
               const float* row_div, void* c, int64_t ldc, int32_t m, int32_t n, void* stream);
 
+/*
+ * Weight gradients on the tcgen05 tensor cores (MN-major operands, split-K over the rows, deterministic):
+ *   out[n, k] = sum_s sum_m a_s[m, n] * b_s[m, k]        n, k <= 256, fp32 output, 1 <= n_src <= 3
+ * a_s = upstream gradient g [m, n], b_s = layer input [m, k], both row-major with 16-byte aligned rows; `srcs[s].k`
+ * is ignored.  Replaces the autograd of /root/reference/module/layer.py:51 for the weights: gW1 = g^T feat[:N_in],
+ * gW2 = g^T ah (one call each; three pairs per call for the split-fp32 product).  `workspace`: fp32 scratch of
+ * pg_wgrad_workspace(m, n, k, dtype_in) floats for the split-K partials.
+ */
+int64_t pg_wgrad_workspace(int32_t m, int32_t n, int32_t k, int dtype_in);
+int pg_wgrad(int dtype_in, const pg_gemm_src* srcs, int32_t n_src, float* out, int64_t ldo, int32_t m, int32_t n,
+             int32_t k, float* workspace, int64_t workspace_floats, void* stream);
+
 /* hi = x with the 13 low mantissa bits cleared (a tf32 value), lo = x - hi (exact); [rows, d] fp32 */
 int pg_split_tf32(const float* x, int64_t ldx, float* hi, float* lo, int64_t ld, int32_t rows, int32_t d,
                   void* stream);

@@ -157,6 +157,8 @@ agg_fixup_kernel(pg_csr g, T* __restrict__ out, int64_t ldo, int nvec, const flo
   }
 }
 
+int g_agg_l2_hint = 1; // pg_set_option("agg_l2_hint", 0|1): L2 eviction policies by source hotness in the chunked kernel
+
 // ---------------------------------------------------------------------------------------------------------
 // v2: chunked walk over the degree-sorted, permuted CSR (pg_csr::chunks / pidx / prow).
 //
@@ -167,9 +169,46 @@ agg_fixup_kernel(pg_csr g, T* __restrict__ out, int64_t ldo, int nvec, const flo
 // one longer row, or one segment of a long row.  One 16-byte descriptor load, then ONE coalesced load fetches the
 // chunk's (next 32) column indices, which are broadcast by shuffles; neighbour rows are fetched U at a time with
 // warp-uniform predicates on the ragged end: the dependent chain per chunk is descriptor -> indices -> rows.
+// L2 residency by source hotness: bit 31 of a permuted column id marks a source row that is referenced often enough
+// to be worth keeping in the 126 MB L2 (the plan marks the most-referenced rows up to a byte budget).  Hot rows are
+// loaded with an evict_last policy, everything that is touched once or rarely (cold rows, the index stream, the
+// output) with evict_first / streaming hints, so that the long tail does not flush the hubs
+// (profiles/r2_gather_micro.jsonl: an L2-resident gather runs at 20 TB/s, a DRAM-bound one at 8).
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+template <int VB> __device__ __forceinline__ typename RawVec<VB>::type ld_vec_policy(const void* p, uint64_t pol);
+template <> __device__ __forceinline__ uint4 ld_vec_policy<16>(const void* p, uint64_t pol) {
+  uint4 v;
+  asm volatile("ld.global.nc.L2::cache_hint.v4.u32 {%0, %1, %2, %3}, [%4], %5;"
+               : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p), "l"(pol));
+  return v;
+}
+template <> __device__ __forceinline__ uint2 ld_vec_policy<8>(const void* p, uint64_t pol) {
+  uint2 v;
+  asm volatile("ld.global.nc.L2::cache_hint.v2.u32 {%0, %1}, [%2], %3;" : "=r"(v.x), "=r"(v.y) : "l"(p), "l"(pol));
+  return v;
+}
+template <> __device__ __forceinline__ uint32_t ld_vec_policy<4>(const void* p, uint64_t pol) {
+  uint32_t v;
+  asm volatile("ld.global.nc.L2::cache_hint.u32 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(pol));
+  return v;
+}
+template <int VB> __device__ __forceinline__ void st_vec_cs(void* p, typename RawVec<VB>::type v);
+template <> __device__ __forceinline__ void st_vec_cs<16>(void* p, uint4 v) { __stcs(reinterpret_cast<uint4*>(p), v); }
+template <> __device__ __forceinline__ void st_vec_cs<8>(void* p, uint2 v) { __stcs(reinterpret_cast<uint2*>(p), v); }
+template <> __device__ __forceinline__ void st_vec_cs<4>(void* p, uint32_t v) { __stcs(reinterpret_cast<uint32_t*>(p), v); }
+
 struct Chunk { int e_beg, n, item, kind_rows; };   // kind = kind_rows & 3 (0: n_rows rows of n edges, 1: one row, 2: segment)
 
-template <typename T, int VB, int VPL, int U>
+template <typename T, int VB, int VPL, int U, bool HINT>
 __global__ void __launch_bounds__(256)
 agg2_kernel(pg_csr g, const T* __restrict__ x, uint32_t ldx_bytes, T* __restrict__ out, int64_t ldo, int nvec,
             const float* __restrict__ row_div, int acc_rows, float* __restrict__ scratch, int64_t lds) {
@@ -181,9 +220,20 @@ agg2_kernel(pg_csr g, const T* __restrict__ x, uint32_t ldx_bytes, T* __restrict
   const int lane = threadIdx.x & 31;
   const int cid = blockIdx.x * 8 + (threadIdx.x >> 5);
   if (cid >= g.n_chunks) return;
-  const int4 c = __ldg(reinterpret_cast<const int4*>(g.chunks) + cid);
+  const int4 c = __ldcs(reinterpret_cast<const int4*>(g.chunks) + cid);
   const int kind = c.w & 3, n_rows = c.w >> 2;
   const uint32_t* __restrict__ pidx = reinterpret_cast<const uint32_t*>(g.pidx) + c.x;
+  uint64_t pol_hot = 0, pol_cold = 0;
+  if (HINT) {
+    pol_hot = l2_policy_evict_last();
+    pol_cold = l2_policy_evict_first();
+  }
+  // one neighbour-row vector; `s` = column id with the hot flag in bit 31
+  auto ld_row = [&](const char* base, uint32_t s) -> Raw {
+    const char* p = base + static_cast<uint64_t>(s & 0x7fffffffu) * ldx_bytes;
+    if (HINT) return ld_vec_policy<VB>(p, (s >> 31) ? pol_hot : pol_cold);
+    return ld_vec<VB>(p);
+  };
 
   for (int c0 = 0; c0 < nvec; c0 += 32 * VPL) {
     float2 acc[VPL][NA];
@@ -213,7 +263,8 @@ agg2_kernel(pg_csr g, const T* __restrict__ x, uint32_t ldx_bytes, T* __restrict
 #pragma unroll
             for (int i = 0; i < V; ++i) r[i] += ov[i];
           }
-          st_vec<VB>(op + o, P::pack(r));
+          if (HINT) st_vec_cs<VB>(op + o, P::pack(r));
+          else st_vec<VB>(op + o, P::pack(r));
         }
 #pragma unroll
         for (int i = 0; i < NA; ++i) acc[j][i] = make_float2(0.f, 0.f);
@@ -222,7 +273,7 @@ agg2_kernel(pg_csr g, const T* __restrict__ x, uint32_t ldx_bytes, T* __restrict
 
     if (kind == 0) {
       const int len = c.y, n_e = len * n_rows;            // n_e <= 32
-      const uint32_t my_idx = lane < n_e ? __ldg(pidx + lane) : 0u;
+      const uint32_t my_idx = lane < n_e ? __ldcs(pidx + lane) : 0u;
       int my_row = 0;
       float my_inv = 1.f;
       if (lane < n_rows) {
@@ -238,7 +289,7 @@ agg2_kernel(pg_csr g, const T* __restrict__ x, uint32_t ldx_bytes, T* __restrict
           if (u0 + u < n_e) {
 #pragma unroll
             for (int j = 0; j < VPL; ++j)
-              if (act[j]) v[u][j] = ld_vec<VB>(xc[j] + static_cast<uint64_t>(s) * ldx_bytes);
+              if (act[j]) v[u][j] = ld_row(xc[j], s);
           }
         }
 #pragma unroll
@@ -259,10 +310,10 @@ agg2_kernel(pg_csr g, const T* __restrict__ x, uint32_t ldx_bytes, T* __restrict
         for (r = 0; r < n_rows; ++r) flush(__shfl_sync(kFull, my_row, r), 1.f);
     } else {
       const int n_e = c.y;
-      uint32_t nxt = lane < n_e ? __ldg(pidx + lane) : 0u;
+      uint32_t nxt = lane < n_e ? __ldcs(pidx + lane) : 0u;
       for (int base = 0; base < n_e; base += 32) {
         const uint32_t my_idx = nxt;
-        if (base + 32 + lane < n_e) nxt = __ldg(pidx + base + 32 + lane);   // next 32 indices while these are used
+        if (base + 32 + lane < n_e) nxt = __ldcs(pidx + base + 32 + lane);  // next 32 indices while these are used
         const int n = min(32, n_e - base);
         int u0 = 0;
         for (; u0 + U <= n; u0 += U) {
@@ -272,7 +323,7 @@ agg2_kernel(pg_csr g, const T* __restrict__ x, uint32_t ldx_bytes, T* __restrict
             const uint32_t s = __shfl_sync(kFull, my_idx, u0 + u);
 #pragma unroll
             for (int j = 0; j < VPL; ++j)
-              if (act[j]) v[u][j] = ld_vec<VB>(xc[j] + static_cast<uint64_t>(s) * ldx_bytes);
+              if (act[j]) v[u][j] = ld_row(xc[j], s);
           }
 #pragma unroll
           for (int u = 0; u < U; ++u)
@@ -288,7 +339,7 @@ agg2_kernel(pg_csr g, const T* __restrict__ x, uint32_t ldx_bytes, T* __restrict
             if (u0 + u < n) {
 #pragma unroll
               for (int j = 0; j < VPL; ++j)
-                if (act[j]) v[u][j] = ld_vec<VB>(xc[j] + static_cast<uint64_t>(s) * ldx_bytes);
+                if (act[j]) v[u][j] = ld_row(xc[j], s);
             }
           }
 #pragma unroll
@@ -323,8 +374,12 @@ static int launch_agg2(const pg_csr& g, const T* x, int64_t ldx, T* out, int64_t
   constexpr int U = (VPL >= 4) ? 2 : (VPL == 2 ? 4 : 8);
   if (g.n_chunks > 0) {
     const unsigned blocks = static_cast<unsigned>((g.n_chunks + 7) / 8);
-    agg2_kernel<T, VB, VPL, U><<<blocks, 256, 0, st>>>(g, x, static_cast<uint32_t>(ldx * sizeof(T)), out, ldo, nvec,
-                                                       row_div, acc_rows, scratch, lds);
+    if (g_agg_l2_hint)
+      agg2_kernel<T, VB, VPL, U, true><<<blocks, 256, 0, st>>>(g, x, static_cast<uint32_t>(ldx * sizeof(T)), out, ldo, nvec,
+                                                               row_div, acc_rows, scratch, lds);
+    else
+      agg2_kernel<T, VB, VPL, U, false><<<blocks, 256, 0, st>>>(g, x, static_cast<uint32_t>(ldx * sizeof(T)), out, ldo, nvec,
+                                                                row_div, acc_rows, scratch, lds);
     PG_LAUNCH_CHECK();
   }
   if (g.n_long > 0) {
@@ -475,6 +530,10 @@ extern "C" int pg_set_option(const char* name, int value) {
   if (strcmp(name, "agg_unroll") == 0) {
     PG_REQUIRE(value == 4 || value == 8, "agg_unroll must be 4 or 8");
     pg::g_agg_unroll = value;
+    return PG_OK;
+  }
+  if (strcmp(name, "agg_l2_hint") == 0) {
+    pg::g_agg_l2_hint = value ? 1 : 0;
     return PG_OK;
   }
   if (strcmp(name, "agg_impl") == 0) {

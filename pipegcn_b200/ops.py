@@ -94,7 +94,7 @@ def sage_aggregate(feat: torch.Tensor, graph: PartGraph, deg_f: torch.Tensor = N
 
 
 # ---- dense part: hand-written tcgen05 GEMM (csrc/linear_tcgen05.cu) -----------------------------
-LINEAR_IMPL = "tcgen05 (pg_linear: TMA + tcgen05.mma kind::f16 / 3xTF32, TMEM accumulators); dW via cuBLAS"
+LINEAR_IMPL = "tcgen05 (pg_linear / pg_wgrad: TMA + tcgen05.mma kind::f16 / 3xTF32, TMEM accumulators; dW MN-major split-K)"
 
 
 def _tma_ready(t: torch.Tensor) -> torch.Tensor:
@@ -175,14 +175,40 @@ def gemm_nt(a0, b0, a1=None, b1=None, bias=None, row_div=None, out=None, out_dty
     return out
 
 
-def _mm_f32(a_t: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
-    """a_t^T-shaped weight gradient  g^T @ x  with fp32 output (library GEMM: a plain cuBLAS call)."""
-    if a_t.dtype == torch.float32:
-        return torch.mm(a_t, b)
-    try:
-        return torch.mm(a_t, b, out_dtype=torch.float32)
-    except (TypeError, RuntimeError):
-        return torch.mm(a_t.float(), b.float())
+_WG_WS = {}
+
+
+def wgrad(g: torch.Tensor, x: torch.Tensor) -> torch.Tensor:
+    """g^T @ x  -> fp32 [n, k]: the weight gradient of `x @ W^T` on the tcgen05 tensor cores (pg_wgrad: MN-major
+    operands straight from the row-major activations, split-K over the rows, fixed-order reduction)."""
+    _rows(g), _rows(x)
+    m, n, k = g.shape[0], g.shape[1], x.shape[1]
+    assert x.shape[0] == m and g.dtype == x.dtype
+    out = torch.empty(n, k, dtype=torch.float32, device=g.device)
+    if m == 0:
+        return out.zero_()
+    if g.dtype == torch.float32 and FP32_GEMM == "3xtf32":
+        (gh, gl), (xh, xl) = split_tf32(g), split_tf32(x)
+        pairs = [(gh, xh), (gh, xl), (gl, xh)]
+    else:
+        pairs = [(_tma_ready(g), _tma_ready(x))]
+    code = _C.dtype_code(g.dtype)
+    for n0 in range(0, n, 256):
+        for k0 in range(0, k, 256):
+            nn, kk = min(256, n - n0), min(256, k - k0)
+            need = int(_C.lib.pg_wgrad_workspace(m, nn, kk, code))
+            ws = _WG_WS.get(g.device)
+            if ws is None or ws.numel() < need:
+                ws = _WG_WS[g.device] = torch.empty(need, dtype=torch.float32, device=g.device)
+            es = g.element_size()
+            srcs = (_C.pg_gemm_src * len(pairs))(*[
+                _C.pg_gemm_src(a.data_ptr() + n0 * es, a.stride(0), b.data_ptr() + k0 * es, b.stride(0), m)
+                for a, b in pairs])
+            o = out[n0:n0 + nn, k0:k0 + kk]
+            _C.count(2)
+            _C.check(_C.lib.pg_wgrad(code, srcs, len(pairs), o.data_ptr(), o.stride(0), m, nn, kk, ws.data_ptr(),
+                                     ws.numel(), _C.stream_ptr()), "pg_wgrad")
+    return out
 
 
 class _Linear(torch.autograd.Function):
@@ -201,7 +227,7 @@ class _Linear(torch.autograd.Function):
         colsum = _take_colsum(g)
         g = _tma_ready(g if g.dtype == x.dtype else g.to(x.dtype))
         gx = gemm_nt(g, padded_weight(weight, x.dtype, transpose=True)) if ctx.needs_input_grad[0] else None
-        gw = _mm_f32(g.t(), x).to(weight.dtype)
+        gw = wgrad(g, x).to(weight.dtype)
         gb = (colsum if colsum is not None else g.float().sum(0)) if ctx.has_bias else None
         return gx, gw, gb
 
@@ -252,9 +278,8 @@ class SageLayerFn(torch.autograd.Function):
             gemm_nt(g, padded_weight(w1, x.dtype, transpose=True), out=g_feat[:graph.num_in])
             gs = gemm_nt(g, padded_weight(w2, x.dtype, transpose=True), row_div=deg_f)
             aggregate(graph.bwd, gs, out=g_feat, acc_rows=graph.num_in)
-        gt = g.t()
-        gw1 = _mm_f32(gt, x).to(w1.dtype)
-        gw2 = _mm_f32(gt, ah).to(w2.dtype)
+        gw1 = wgrad(g, x).to(w1.dtype)
+        gw2 = wgrad(g, ah).to(w2.dtype)
         gb = (colsum if colsum is not None else g.float().sum(0)) if ctx.has_bias else None
         return g_feat, None, None, gw1, gb, gw2, gb
 

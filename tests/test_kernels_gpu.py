@@ -282,3 +282,25 @@ def test_chunked_kernel_equals_row_kernel(dtype, d):
     ref = _ref_agg(indptr, indices, x.float().cpu(), div.cpu())
     tol = 2e-5 if dtype == torch.float32 else 1.6e-2
     assert (outs[1][0].float().cpu().double() - ref).abs().max().item() <= tol * ref.abs().max().item() + 1e-6
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
+@pytest.mark.parametrize("m,n,k", [(5000, 256, 256), (70000, 256, 256), (3000, 64, 256), (2500, 41, 602), (1, 16, 8),
+                                   (63, 128, 100), (12345, 200, 1204)])
+def test_wgrad_matches_torch(dtype, m, n, k):
+    """pg_wgrad (MN-major tcgen05, split-K over the rows) == g^T @ x in fp64: bf16 exact products with fp32
+    accumulation (rel. 1e-5 of the output scale), fp32 through the 3xTF32 product (rel. 3e-5)."""
+    from pipegcn_b200 import ops
+    from pipegcn_b200.graph import alloc_rows
+    gen = torch.Generator().manual_seed(m + n + k)
+    g = alloc_rows(m, n, dtype, DEV, zero=True)
+    x = alloc_rows(m, k, dtype, DEV, zero=True)
+    g.copy_(torch.randn(m, n, generator=gen).to(dtype))
+    x.copy_(torch.randn(m, k, generator=gen).to(dtype))
+    out = ops.wgrad(g, x)
+    assert out.shape == (n, k) and out.dtype == torch.float32
+    ref = g.double().cpu().t() @ x.double().cpu()
+    err = (out.double().cpu() - ref).abs().max().item()
+    assert err <= 3e-5 * max(ref.abs().max().item(), 1.0) + 1e-6, (err, ref.abs().max().item())
+    # deterministic: same partials, same order
+    assert torch.equal(out, ops.wgrad(g, x))
