@@ -70,7 +70,9 @@ typedef struct pg_csr {
                                  *   kind 1: one row of n entries, item = its position in prow
                                  *   kind 2: one segment (n entries) of a long row, item = segment index (scratch slot) */
   int32_t n_chunks;
-  const int32_t* pidx;          /* [nnz] column ids, rows concatenated in processing order */
+  int32_t n_chunks_long;        /* the kind 2 and kind 1 chunks come first: chunks [0, n_chunks_long) */
+  const int32_t* pidx;          /* [nnz] column ids, rows concatenated in processing order; bit 31 set = "hot" source
+                                 * row (referenced often): loaded with an L2 evict_last policy */
   const int32_t* prow;          /* [n_rows] row id of every position of the processing order */
 } pg_csr;
 

@@ -24,7 +24,8 @@ class pg_csr(C.Structure):
     _fields_ = [("indptr", C.c_void_p), ("indices", C.c_void_p), ("n_rows", C.c_int32), ("seg_len", C.c_int32),
                 ("n_long", C.c_int32), ("n_seg", C.c_int32), ("long_row", C.c_void_p), ("long_seg_ptr", C.c_void_p),
                 ("seg_long", C.c_void_p), ("row_order", C.c_void_p), ("nnz", C.c_int64),
-                ("chunks", C.c_void_p), ("n_chunks", C.c_int32), ("pidx", C.c_void_p), ("prow", C.c_void_p)]
+                ("chunks", C.c_void_p), ("n_chunks", C.c_int32), ("n_chunks_long", C.c_int32),
+                ("pidx", C.c_void_p), ("prow", C.c_void_p)]
 
 
 class pg_gemm_src(C.Structure):
@@ -83,7 +84,8 @@ def _load():
 
 lib, EXPORTS = _load()
 for _k, _v in (("agg_unroll", os.environ.get("PG_AGG_UNROLL")), ("agg_pack_short", os.environ.get("PG_AGG_PACK")),
-               ("agg_impl", os.environ.get("PG_AGG_IMPL"))):
+               ("agg_impl", os.environ.get("PG_AGG_IMPL")), ("agg_l2_hint", os.environ.get("PG_AGG_L2_HINT")),
+               ("agg_occ", os.environ.get("PG_AGG_OCC"))):
     if _v:
         lib.pg_set_option(_k.encode(), int(_v))
 

@@ -157,6 +157,8 @@ agg_fixup_kernel(pg_csr g, T* __restrict__ out, int64_t ldo, int nvec, const flo
   }
 }
 
+int g_agg_unroll = 8;   // pg_set_option("agg_unroll", 4|8): neighbour rows in flight per group (VPL == 1, agg_impl 1)
+int g_agg_occ = 4;      // pg_set_option("agg_occ", 4|5): resident CTAs per SM the long-row kernel is compiled for (64 / 48 registers)
 int g_agg_l2_hint = 1; // pg_set_option("agg_l2_hint", 0|1): L2 eviction policies by source hotness in the chunked kernel
 
 // ---------------------------------------------------------------------------------------------------------
@@ -209,177 +211,240 @@ template <> __device__ __forceinline__ void st_vec_cs<4>(void* p, uint32_t v) { 
 struct Chunk { int e_beg, n, item, kind_rows; };   // kind = kind_rows & 3 (0: n_rows rows of n edges, 1: one row, 2: segment)
 
 template <typename T, int VB, int VPL, int U, bool HINT>
-__global__ void __launch_bounds__(256)
-agg2_kernel(pg_csr g, const T* __restrict__ x, uint32_t ldx_bytes, T* __restrict__ out, int64_t ldo, int nvec,
-            const float* __restrict__ row_div, int acc_rows, float* __restrict__ scratch, int64_t lds) {
+struct Agg2 {
   using P = Pack<T, VB>;
   using Raw = typename P::Raw;
-  constexpr int V = P::V;
-  constexpr int NA = P::NA;
-  constexpr unsigned kFull = 0xffffffffu;
-  const int lane = threadIdx.x & 31;
-  const int cid = blockIdx.x * 8 + (threadIdx.x >> 5);
-  if (cid >= g.n_chunks) return;
-  const int4 c = __ldcs(reinterpret_cast<const int4*>(g.chunks) + cid);
-  const int kind = c.w & 3, n_rows = c.w >> 2;
-  const uint32_t* __restrict__ pidx = reinterpret_cast<const uint32_t*>(g.pidx) + c.x;
-  uint64_t pol_hot = 0, pol_cold = 0;
-  if (HINT) {
-    pol_hot = l2_policy_evict_last();
-    pol_cold = l2_policy_evict_first();
-  }
-  // one neighbour-row vector; `s` = column id with the hot flag in bit 31
-  auto ld_row = [&](const char* base, uint32_t s) -> Raw {
-    const char* p = base + static_cast<uint64_t>(s & 0x7fffffffu) * ldx_bytes;
-    if (HINT) return ld_vec_policy<VB>(p, (s >> 31) ? pol_hot : pol_cold);
-    return ld_vec<VB>(p);
-  };
+  static constexpr int V = P::V;
+  static constexpr int NA = P::NA;
+  static constexpr int kVPL = VPL;
+  static constexpr unsigned kFull = 0xffffffffu;
 
-  for (int c0 = 0; c0 < nvec; c0 += 32 * VPL) {
-    float2 acc[VPL][NA];
-    bool act[VPL];
-    const char* xc[VPL];
+  const char* xc[VPL];      // this lane's column(s) of source row 0
+  bool act[VPL];
+  uint32_t ldx_bytes;
+  uint64_t pol_hot, pol_cold;
+  T* out;
+  int64_t ldo;
+  int col0;                 // first vector column of this lane (c0 + lane)
+  int acc_rows;
+  float2 acc[VPL][NA];
+
+  __device__ __forceinline__ void zero() {
 #pragma unroll
-    for (int j = 0; j < VPL; ++j) {
+    for (int j = 0; j < VPL; ++j)
 #pragma unroll
       for (int i = 0; i < NA; ++i) acc[j][i] = make_float2(0.f, 0.f);
-      const int vi = c0 + lane + j * 32;
-      act[j] = vi < nvec;
-      xc[j] = reinterpret_cast<const char*>(x + static_cast<int64_t>(vi) * V);
+  }
+  // one neighbour-row vector; `s` = column id with the hot flag in bit 31
+  __device__ __forceinline__ Raw ld_row(int j, uint32_t s) const {
+    const char* p = xc[j] + static_cast<uint64_t>(s & 0x7fffffffu) * ldx_bytes;
+    if (HINT) return ld_vec_policy<VB>(p, (s >> 31) ? pol_hot : pol_cold);
+    return ld_vec<VB>(p);
+  }
+  // lanes past the row width (act[j] false) read column 0 like lane 0 does (same address: no extra traffic) and
+  // are only masked at the store: the loads and adds of the inner loops carry no predicates
+  __device__ __forceinline__ void add(const Raw (&v)[VPL]) {
+#pragma unroll
+    for (int j = 0; j < VPL; ++j) P::add(acc[j], v[j]);
+  }
+  // the ragged end of a batch: every load is issued (positions past the end fetch a valid row: lanes past the
+  // chunk hold column 0) and the fetched bits are ANDed with 0 / ~0 -- no predicated loads, no divergent code
+  __device__ __forceinline__ void add_masked(const Raw (&v)[VPL], bool keep) {
+    const uint32_t m = keep ? 0xffffffffu : 0u;
+#pragma unroll
+    for (int j = 0; j < VPL; ++j) {
+      Raw t = v[j];
+      uint32_t* w = reinterpret_cast<uint32_t*>(&t);
+#pragma unroll
+      for (int i = 0; i < VB / 4; ++i) w[i] &= m;
+      P::add(acc[j], t);
     }
-    // out[row] = acc * inv (+ out[row] when row < acc_rows), then acc = 0
-    auto flush = [&](int row, float inv) {
-      T* op = out + static_cast<int64_t>(row) * ldo;
+  }
+  __device__ __forceinline__ void ld_rows(Raw (&v)[VPL], uint32_t s) const {
+#pragma unroll
+    for (int j = 0; j < VPL; ++j) v[j] = ld_row(j, s);
+  }
+  // out[row] = acc * inv (+ out[row] when row < acc_rows); acc = 0
+  __device__ __forceinline__ void flush(int row, float inv) {
+    T* op = out + static_cast<int64_t>(row) * ldo;
+#pragma unroll
+    for (int j = 0; j < VPL; ++j) {
+      if (act[j]) {
+        const int64_t o = static_cast<int64_t>(col0 + j * 32) * V;
+        float r[V];
+#pragma unroll
+        for (int i = 0; i < V; ++i) r[i] = ((i & 1) ? acc[j][i / 2].y : acc[j][i / 2].x) * inv;
+        if (row < acc_rows) {
+          float ov[V];
+          P::unpack(*reinterpret_cast<const Raw*>(op + o), ov);
+#pragma unroll
+          for (int i = 0; i < V; ++i) r[i] += ov[i];
+        }
+        if (HINT) st_vec_cs<VB>(op + o, P::pack(r));
+        else st_vec<VB>(op + o, P::pack(r));
+      }
+    }
+    zero();
+  }
+
+  // a chunk of n_rows whole rows of `len` (<= 32) entries each, n_rows * len <= 32: U neighbour rows in flight
+  // across row boundaries; a row is flushed as soon as its last entry has been added (warp-uniform branch)
+  __device__ __forceinline__ void small_chunk(uint32_t my_idx, int my_row, float my_inv, int n_rows, int len) {
+    const int n_e = n_rows * len;
+    int r = 0, cnt = 0;
+#pragma unroll 1
+    for (int u0 = 0; u0 < n_e; u0 += U) {
+      Raw v[U][VPL];
+#pragma unroll
+      for (int u = 0; u < U; ++u) ld_rows(v[u], __shfl_sync(kFull, my_idx, (u0 + u) & 31));   // lanes >= n_e hold 0
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        if (u0 + u < n_e) {
+          add(v[u]);
+          if (++cnt == len) {
+            flush(__shfl_sync(kFull, my_row, r), __shfl_sync(kFull, my_inv, r));
+            ++r;
+            cnt = 0;
+          }
+        }
+      }
+    }
+    if (len == 0)                                          // rows without entries: the empty sum
+      for (r = 0; r < n_rows; ++r) flush(__shfl_sync(kFull, my_row, r), 1.f);
+  }
+
+  // B neighbour rows (columns my_idx[u0 .. u0+B) of the current 32 indices) fetched, then added in order
+  template <int B>
+  __device__ __forceinline__ void batch(uint32_t my_idx, int u0) {
+    Raw v[B][VPL];
+#pragma unroll
+    for (int u = 0; u < B; ++u) ld_rows(v[u], __shfl_sync(kFull, my_idx, u0 + u));
+#pragma unroll
+    for (int u = 0; u < B; ++u) add(v[u]);
+  }
+
+  // one row / one segment of n_e entries: 32 indices per coalesced load (the next 32 prefetched), U rows in flight
+  __device__ __forceinline__ void long_row(const uint32_t* __restrict__ pidx, int n_e, int lane) {
+    uint32_t nxt = lane < n_e ? __ldcs(pidx + lane) : 0u;
+#pragma unroll 1
+    for (int base = 0; base < n_e; base += 32) {
+      const uint32_t my_idx = nxt;
+      if (base + 32 + lane < n_e) nxt = __ldcs(pidx + base + 32 + lane);
+      const int n = min(32, n_e - base);
+      int u0 = 0;
+#pragma unroll 1
+      for (; u0 + U <= n; u0 += U) batch<U>(my_idx, u0);
+      // ragged end of the row: 4 + 2 + 1 neighbour rows, no predicated loads
+      if (n - u0 >= 4) { batch<4>(my_idx, u0); u0 += 4; }
+      if (n - u0 >= 2) { batch<2>(my_idx, u0); u0 += 2; }
+      if (n - u0 >= 1) { batch<1>(my_idx, u0); }
+    }
+  }
+};
+
+template <typename A, typename T>
+__device__ __forceinline__ void agg2_setup(A& a, const T* x, uint32_t ldx_bytes, T* out, int64_t ldo, int acc_rows) {
+  a.ldx_bytes = ldx_bytes;
+  a.out = out;
+  a.ldo = ldo;
+  a.acc_rows = acc_rows;
+  a.pol_hot = a.pol_cold = 0;
+}
+template <typename A, typename T>
+__device__ __forceinline__ void agg2_columns(A& a, const T* x, int c0, int lane, int nvec) {
+  a.col0 = c0 + lane;
+#pragma unroll
+  for (int j = 0; j < A::kVPL; ++j) {
+    const int vi = c0 + lane + j * 32;
+    a.act[j] = vi < nvec;
+    a.xc[j] = reinterpret_cast<const char*>(x + static_cast<int64_t>(a.act[j] ? vi : 0) * A::V);
+  }
+  a.zero();
+}
+
+// chunks [0, n_chunks_long): one row (kind 1) or one segment of a long row (kind 2) per warp
+template <typename T, int VB, int VPL, int U, bool HINT, int OCC>
+__global__ void __launch_bounds__(256, (VPL == 1 ? OCC : (VPL == 2 ? 2 : 1)))
+agg2_long_kernel(pg_csr g, const T* __restrict__ x, uint32_t ldx_bytes, T* __restrict__ out, int64_t ldo, int nvec,
+                 const float* __restrict__ row_div, int acc_rows, float* __restrict__ scratch, int64_t lds) {
+  using A = Agg2<T, VB, VPL, U, HINT>;
+  constexpr int V = A::V;
+  const int lane = threadIdx.x & 31;
+  const int cid = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (cid >= g.n_chunks_long) return;
+  const int4 c = __ldcs(reinterpret_cast<const int4*>(g.chunks) + cid);
+  const uint32_t* __restrict__ pidx = reinterpret_cast<const uint32_t*>(g.pidx) + c.x;
+  A a;
+  agg2_setup(a, x, ldx_bytes, out, ldo, acc_rows);
+  if (HINT) {
+    a.pol_hot = l2_policy_evict_last();
+    a.pol_cold = l2_policy_evict_first();
+  }
+  for (int c0 = 0; c0 < nvec; c0 += 32 * VPL) {
+    agg2_columns(a, x, c0, lane, nvec);
+    a.long_row(pidx, c.y, lane);
+    if ((c.w & 3) == 2) {
+      float* sp = scratch + static_cast<int64_t>(c.z) * lds;
 #pragma unroll
       for (int j = 0; j < VPL; ++j) {
-        if (act[j]) {
-          const int64_t o = static_cast<int64_t>(c0 + lane + j * 32) * V;
-          float r[V];
+        if (!a.act[j]) continue;
+        const int64_t o = static_cast<int64_t>(c0 + lane + j * 32) * V;
 #pragma unroll
-          for (int i = 0; i < V; ++i) r[i] = ((i & 1) ? acc[j][i / 2].y : acc[j][i / 2].x) * inv;
-          if (row < acc_rows) {
-            float ov[V];
-            P::unpack(*reinterpret_cast<const Raw*>(op + o), ov);
-#pragma unroll
-            for (int i = 0; i < V; ++i) r[i] += ov[i];
-          }
-          if (HINT) st_vec_cs<VB>(op + o, P::pack(r));
-          else st_vec<VB>(op + o, P::pack(r));
-        }
-#pragma unroll
-        for (int i = 0; i < NA; ++i) acc[j][i] = make_float2(0.f, 0.f);
+        for (int i = 0; i < V; ++i) sp[o + i] = (i & 1) ? a.acc[j][i / 2].y : a.acc[j][i / 2].x;
       }
-    };
-
-    if (kind == 0) {
-      const int len = c.y, n_e = len * n_rows;            // n_e <= 32
-      const uint32_t my_idx = lane < n_e ? __ldcs(pidx + lane) : 0u;
-      int my_row = 0;
-      float my_inv = 1.f;
-      if (lane < n_rows) {
-        my_row = __ldg(g.prow + c.z + lane);
-        if (row_div != nullptr) my_inv = 1.f / __ldg(row_div + my_row);
-      }
-      int r = 0, cnt = 0;
-      for (int u0 = 0; u0 < n_e; u0 += U) {
-        Raw v[U][VPL];
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-          const uint32_t s = __shfl_sync(kFull, my_idx, (u0 + u) & 31);
-          if (u0 + u < n_e) {
-#pragma unroll
-            for (int j = 0; j < VPL; ++j)
-              if (act[j]) v[u][j] = ld_row(xc[j], s);
-          }
-        }
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-          if (u0 + u < n_e) {
-#pragma unroll
-            for (int j = 0; j < VPL; ++j)
-              if (act[j]) P::add(acc[j], v[u][j]);
-            if (++cnt == len) {
-              flush(__shfl_sync(kFull, my_row, r), __shfl_sync(kFull, my_inv, r));
-              ++r;
-              cnt = 0;
-            }
-          }
-        }
-      }
-      if (len == 0)                                       // rows without entries: the empty sum
-        for (r = 0; r < n_rows; ++r) flush(__shfl_sync(kFull, my_row, r), 1.f);
     } else {
-      const int n_e = c.y;
-      uint32_t nxt = lane < n_e ? __ldcs(pidx + lane) : 0u;
-      for (int base = 0; base < n_e; base += 32) {
-        const uint32_t my_idx = nxt;
-        if (base + 32 + lane < n_e) nxt = __ldcs(pidx + base + 32 + lane);  // next 32 indices while these are used
-        const int n = min(32, n_e - base);
-        int u0 = 0;
-        for (; u0 + U <= n; u0 += U) {
-          Raw v[U][VPL];
-#pragma unroll
-          for (int u = 0; u < U; ++u) {
-            const uint32_t s = __shfl_sync(kFull, my_idx, u0 + u);
-#pragma unroll
-            for (int j = 0; j < VPL; ++j)
-              if (act[j]) v[u][j] = ld_row(xc[j], s);
-          }
-#pragma unroll
-          for (int u = 0; u < U; ++u)
-#pragma unroll
-            for (int j = 0; j < VPL; ++j)
-              if (act[j]) P::add(acc[j], v[u][j]);
-        }
-        if (u0 < n) {                                     // ragged end of the row: one predicated batch
-          Raw v[U][VPL];
-#pragma unroll
-          for (int u = 0; u < U; ++u) {
-            const uint32_t s = __shfl_sync(kFull, my_idx, (u0 + u) & 31);
-            if (u0 + u < n) {
-#pragma unroll
-              for (int j = 0; j < VPL; ++j)
-                if (act[j]) v[u][j] = ld_row(xc[j], s);
-            }
-          }
-#pragma unroll
-          for (int u = 0; u < U; ++u)
-            if (u0 + u < n) {
-#pragma unroll
-              for (int j = 0; j < VPL; ++j)
-                if (act[j]) P::add(acc[j], v[u][j]);
-            }
-        }
-      }
-      if (kind == 2) {
-        float* sp = scratch + static_cast<int64_t>(c.z) * lds;
-#pragma unroll
-        for (int j = 0; j < VPL; ++j) {
-          if (!act[j]) continue;
-          const int64_t o = static_cast<int64_t>(c0 + lane + j * 32) * V;
-#pragma unroll
-          for (int i = 0; i < V; ++i) sp[o + i] = (i & 1) ? acc[j][i / 2].y : acc[j][i / 2].x;
-        }
-      } else {
-        const int row = __ldg(g.prow + c.z);
-        flush(row, row_div != nullptr ? 1.f / __ldg(row_div + row) : 1.f);
-      }
+      const int row = __ldg(g.prow + c.z);
+      a.flush(row, row_div != nullptr ? 1.f / __ldg(row_div + row) : 1.f);
     }
   }
 }
 
-template <typename T, int VB, int VPL>
-static int launch_agg2(const pg_csr& g, const T* x, int64_t ldx, T* out, int64_t ldo, int nvec,
-                       const float* row_div, int acc_rows, float* scratch, int64_t lds, cudaStream_t st) {
+// chunks [n_chunks_long, n_chunks): n_rows whole rows of equal length (<= 32 entries together) per warp
+template <typename T, int VB, int VPL, int U, bool HINT>
+__global__ void __launch_bounds__(256, (VPL == 1 ? 3 : (VPL == 2 ? 2 : 1)))
+agg2_small_kernel(pg_csr g, const T* __restrict__ x, uint32_t ldx_bytes, T* __restrict__ out, int64_t ldo, int nvec,
+                  const float* __restrict__ row_div, int acc_rows) {
+  using A = Agg2<T, VB, VPL, U, HINT>;
+  const int lane = threadIdx.x & 31;
+  const int cid = g.n_chunks_long + blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (cid >= g.n_chunks) return;
+  const int4 c = __ldcs(reinterpret_cast<const int4*>(g.chunks) + cid);
+  const int n_rows = c.w >> 2, len = c.y, n_e = len * n_rows;
+  const uint32_t my_idx = lane < n_e ? __ldcs(reinterpret_cast<const uint32_t*>(g.pidx) + c.x + lane) : 0u;
+  int my_row = 0;
+  float my_inv = 1.f;
+  if (lane < n_rows) {
+    my_row = __ldg(g.prow + c.z + lane);
+    if (row_div != nullptr) my_inv = 1.f / __ldg(row_div + my_row);
+  }
+  A a;
+  agg2_setup(a, x, ldx_bytes, out, ldo, acc_rows);
+  if (HINT) {
+    a.pol_hot = l2_policy_evict_last();
+    a.pol_cold = l2_policy_evict_first();
+  }
+  for (int c0 = 0; c0 < nvec; c0 += 32 * VPL) {
+    agg2_columns(a, x, c0, lane, nvec);
+    a.small_chunk(my_idx, my_row, my_inv, n_rows, len);
+  }
+}
+
+template <typename T, int VB, int VPL, bool HINT>
+static int launch_agg2h(const pg_csr& g, const T* x, int64_t ldx, T* out, int64_t ldo, int nvec,
+                        const float* row_div, int acc_rows, float* scratch, int64_t lds, cudaStream_t st) {
   constexpr int U = (VPL >= 4) ? 2 : (VPL == 2 ? 4 : 8);
-  if (g.n_chunks > 0) {
-    const unsigned blocks = static_cast<unsigned>((g.n_chunks + 7) / 8);
-    if (g_agg_l2_hint)
-      agg2_kernel<T, VB, VPL, U, true><<<blocks, 256, 0, st>>>(g, x, static_cast<uint32_t>(ldx * sizeof(T)), out, ldo, nvec,
-                                                               row_div, acc_rows, scratch, lds);
+  const uint32_t ldxb = static_cast<uint32_t>(ldx * sizeof(T));
+  if (g.n_chunks_long > 0) {
+    const unsigned blocks = static_cast<unsigned>((g.n_chunks_long + 7) / 8);
+    if (VPL == 1 && g_agg_occ == 5)
+      agg2_long_kernel<T, VB, VPL, U, HINT, (VPL == 1 ? 5 : 4)><<<blocks, 256, 0, st>>>(g, x, ldxb, out, ldo, nvec, row_div, acc_rows, scratch, lds);
     else
-      agg2_kernel<T, VB, VPL, U, false><<<blocks, 256, 0, st>>>(g, x, static_cast<uint32_t>(ldx * sizeof(T)), out, ldo, nvec,
-                                                                row_div, acc_rows, scratch, lds);
+      agg2_long_kernel<T, VB, VPL, U, HINT, 4><<<blocks, 256, 0, st>>>(g, x, ldxb, out, ldo, nvec, row_div, acc_rows, scratch, lds);
+    PG_LAUNCH_CHECK();
+  }
+  if (g.n_chunks > g.n_chunks_long) {
+    const unsigned blocks = static_cast<unsigned>((g.n_chunks - g.n_chunks_long + 7) / 8);
+    agg2_small_kernel<T, VB, VPL, U, HINT><<<blocks, 256, 0, st>>>(g, x, ldxb, out, ldo, nvec, row_div, acc_rows);
     PG_LAUNCH_CHECK();
   }
   if (g.n_long > 0) {
@@ -389,7 +454,13 @@ static int launch_agg2(const pg_csr& g, const T* x, int64_t ldx, T* out, int64_t
   return PG_OK;
 }
 
-int g_agg_unroll = 8;   // pg_set_option("agg_unroll", 4|8): neighbour rows in flight per group (VPL == 1)
+template <typename T, int VB, int VPL>
+static int launch_agg2(const pg_csr& g, const T* x, int64_t ldx, T* out, int64_t ldo, int nvec,
+                       const float* row_div, int acc_rows, float* scratch, int64_t lds, cudaStream_t st) {
+  if (g_agg_l2_hint) return launch_agg2h<T, VB, VPL, true>(g, x, ldx, out, ldo, nvec, row_div, acc_rows, scratch, lds, st);
+  return launch_agg2h<T, VB, VPL, false>(g, x, ldx, out, ldo, nvec, row_div, acc_rows, scratch, lds, st);
+}
+
 int g_agg_impl = 2;     // pg_set_option("agg_impl", 1|2): 1 = row-per-group kernel, 2 = chunked kernel (needs pg_csr::chunks)
 int g_agg_pack_short = 0;   // pg_set_option("agg_pack_short", 0|1): 16 lanes x 2 vectors per row when rows are short.
                             // OFF: measured slower (tools/agg_micro.py, P=8 partition: bwd 277 -> 312 us)
@@ -530,6 +601,11 @@ extern "C" int pg_set_option(const char* name, int value) {
   if (strcmp(name, "agg_unroll") == 0) {
     PG_REQUIRE(value == 4 || value == 8, "agg_unroll must be 4 or 8");
     pg::g_agg_unroll = value;
+    return PG_OK;
+  }
+  if (strcmp(name, "agg_occ") == 0) {
+    PG_REQUIRE(value == 4 || value == 5, "agg_occ must be 4 or 5");
+    pg::g_agg_occ = value;
     return PG_OK;
   }
   if (strcmp(name, "agg_l2_hint") == 0) {

@@ -20,7 +20,7 @@ class CsrPlan:
     """Device CSR + the split of its long rows, packaged as a `pg_csr` for the C ABI."""
 
     def __init__(self, indptr: torch.Tensor, indices: torch.Tensor, seg_len: Optional[int] = None,
-                 sort_rows: bool = True):
+                 sort_rows: bool = True, row_bytes_hint: int = 512):
         assert indptr.dtype == torch.int32 and indices.dtype == torch.int32
         self.indptr, self.indices = indptr.contiguous(), indices.contiguous()
         self.n_rows = int(indptr.numel() - 1)
@@ -51,7 +51,8 @@ class CsrPlan:
         self.max_deg = int(deg.max().item()) if self.n_rows else 0
         self._scratch = None
         self.chunks = self.pidx = self.prow = None
-        self.n_chunks = 0
+        self.n_chunks = self.n_chunks_long = self.n_hot = 0
+        self.row_bytes_hint = int(row_bytes_hint)
         if self.n_rows and sort_rows and int(os.environ.get("PG_AGG_CHUNKS", "1")):
             self._build_chunks(order, ldeg, n_long, nseg)
         self.c = _C.pg_csr(self.indptr.data_ptr(), self.indices.data_ptr(), self.n_rows, self.seg_len, n_long,
@@ -59,7 +60,7 @@ class CsrPlan:
                            self.seg_long.data_ptr(),
                            self.row_order.data_ptr() if self.row_order is not None else None, self.nnz,
                            self.chunks.data_ptr() if self.chunks is not None else None, self.n_chunks,
-                           self.pidx.data_ptr() if self.pidx is not None else None,
+                           self.n_chunks_long, self.pidx.data_ptr() if self.pidx is not None else None,
                            self.prow.data_ptr() if self.prow is not None else None)
 
     def _build_chunks(self, order, ldeg, n_long, nseg):
@@ -71,7 +72,21 @@ class CsrPlan:
         if self.nnz:
             start = self.indptr.to(torch.int64)[order]
             pos = torch.repeat_interleave(start - pptr[:-1], ldeg) + torch.arange(self.nnz, **i64)
-            self.pidx = self.indices[pos].contiguous()
+            pidx = self.indices[pos]
+            # "hot" source rows: the most referenced ones, as many as fit a byte budget of the L2 (126 MB); the kernel
+            # loads them with an evict_last policy and everything else with evict_first (bit 31 of the column id)
+            budget_rows = int(float(os.environ.get("PG_HOT_MB", "64")) * 2 ** 20) // max(self.row_bytes_hint, 1)
+            refs = torch.bincount(self.indices.to(torch.int64))
+            if budget_rows > 0:
+                if refs.numel() > budget_rows:
+                    kth = torch.topk(refs, budget_rows, sorted=True).values[-1]
+                    hot = refs >= torch.clamp(kth, min=2)
+                else:
+                    hot = refs >= 2
+                self.n_hot = int(hot.sum().item())
+                flag = torch.tensor(-2 ** 31, dtype=torch.int32, device=dev)
+                pidx = torch.where(hot[pidx.to(torch.int64)], pidx | flag, pidx)
+            self.pidx = pidx.contiguous()
         else:
             self.pidx = torch.zeros(1, dtype=torch.int32, device=dev)
         self.prow = order.to(torch.int32).contiguous()
@@ -100,6 +115,7 @@ class CsrPlan:
                 rows = torch.clamp(a + m - first, max=per)
                 parts.append(torch.stack([pptr[first], torch.full_like(first, length), first, rows << 2], 1))
                 a += m
+        self.n_chunks_long = self.n_seg + max(0, n_mid_end - n_long)
         tab = torch.cat(parts, 0) if parts else torch.zeros(0, 4, **i64)
         self.chunks = tab.to(torch.int32).contiguous()
         self.n_chunks = int(tab.shape[0])

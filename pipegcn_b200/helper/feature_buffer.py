@@ -330,7 +330,9 @@ class Buffer(object):
         if int(self._status.item()) != 0:
             self._status.zero_()
             raise _C.PgError("halo exchange: a peer's flag did not arrive within "
-                             f"{self.timeout_ms} ms (PG_ERR_TIMEOUT)")
+                             f"{self.timeout_ms} ms (PG_ERR_TIMEOUT); rank {self._world.rank} epoch {self._epoch} "
+                             f"pipeline={self._pipeline} static0={self._static0_ready} received flags "
+                             f"[layer][fwd,bwd][source rank] = {self._flags.tolist()}")
 
     # ------------------------------------------------------------------ kernels
     def _push(self, ms: Optional[_MsgSet], src: torch.Tensor, d: int, offset: int):

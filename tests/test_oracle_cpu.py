@@ -89,7 +89,7 @@ def test_c_abi_exports_every_declared_symbol():
     lib_path = build(verbose=False)
     lib = ctypes.CDLL(str(lib_path))
     header = (ROOT / "include" / "pipegcn_b200.h").read_text()
-    names = re.findall(r"^\s*(?:int|const char\*)\s+(pg_[a-z0-9_]+)\s*\(", header, flags=re.M)
+    names = re.findall(r"^\s*(?:int|int64_t|const char\*)\s+(pg_[a-z0-9_]+)\s*\(", header, flags=re.M)
     assert len(names) >= 14
     for n in names:
         assert hasattr(lib, n), f"{n} declared in the header but not exported"
