@@ -118,7 +118,7 @@ int pg_linear(int dtype_in, int dtype_out, const pg_gemm_src* srcs, int32_t n_sr
 
 /*
  * Weight gradients on the tcgen05 tensor cores (MN-major operands, split-K over the rows, deterministic):
- *   out[n, k] = sum_s sum_m a_s[m, n] * b_s[m, k]        n, k <= 256, fp32 output, 1 <= n_src <= 3
+ *   out[n, k] = sum_s sum_m a_s[m, n] * b_s[m, k]        n, k <= 256, fp32 output, 1 <= n_src <= 6
  * a_s = upstream gradient g [m, n], b_s = layer input [m, k], both row-major with 16-byte aligned rows; `srcs[s].k`
  * is ignored.  Replaces the autograd of /root/reference/module/layer.py:51 for the weights: gW1 = g^T feat[:N_in],
  * gW2 = g^T ah (one call each; three pairs per call for the split-fp32 product).  `workspace`: fp32 scratch of

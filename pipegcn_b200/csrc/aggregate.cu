@@ -124,27 +124,41 @@ agg_kernel(pg_csr g, const T* __restrict__ x, uint32_t ldx_bytes, T* __restrict_
   }
 }
 
-// sums the fp32 partials of every long row in segment order and writes the row
+// sums the fp32 partials of every long row in segment order and writes the row: one warp per long row, four
+// partials in flight
 template <typename T, int VB>
 __global__ void __launch_bounds__(256)
 agg_fixup_kernel(pg_csr g, T* __restrict__ out, int64_t ldo, int nvec, const float* __restrict__ row_div,
                  int acc_rows, const float* __restrict__ scratch, int64_t lds) {
   using P = Pack<T, VB>;
   constexpr int V = P::V;
-  const int li = blockIdx.x;
-  const int row = g.long_row[li];
-  const int s0 = g.long_seg_ptr[li], s1 = g.long_seg_ptr[li + 1];
-  const float inv = row_div ? 1.f / row_div[row] : 1.f;
+  const int li = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (li >= g.n_long) return;
+  const int lane = threadIdx.x & 31;
+  const int row = __ldg(g.long_row + li);
+  const int s0 = __ldg(g.long_seg_ptr + li), s1 = __ldg(g.long_seg_ptr + li + 1);
+  const float inv = row_div ? 1.f / __ldg(row_div + row) : 1.f;
   T* op = out + static_cast<int64_t>(row) * ldo;
-  for (int vi = threadIdx.x; vi < nvec; vi += blockDim.x) {
+  for (int vi = lane; vi < nvec; vi += 32) {
     float r[V];
 #pragma unroll
     for (int i = 0; i < V; ++i) r[i] = 0.f;
-    for (int s = s0; s < s1; ++s) {
-      const float* sp = scratch + static_cast<int64_t>(s) * lds + static_cast<int64_t>(vi) * V;
+    const float* sp = scratch + static_cast<int64_t>(vi) * V;
+    int s = s0;
+    for (; s + 4 <= s1; s += 4) {
+      float t[4][V];
 #pragma unroll
-      for (int i = 0; i < V; ++i) r[i] += sp[i];
+      for (int u = 0; u < 4; ++u)
+#pragma unroll
+        for (int i = 0; i < V; ++i) t[u][i] = __ldcs(sp + static_cast<int64_t>(s + u) * lds + i);
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+#pragma unroll
+        for (int i = 0; i < V; ++i) r[i] += t[u][i];
     }
+    for (; s < s1; ++s)
+#pragma unroll
+      for (int i = 0; i < V; ++i) r[i] += __ldcs(sp + static_cast<int64_t>(s) * lds + i);
 #pragma unroll
     for (int i = 0; i < V; ++i) r[i] *= inv;
     if (row < acc_rows) {
@@ -157,6 +171,8 @@ agg_fixup_kernel(pg_csr g, T* __restrict__ out, int64_t ldo, int nvec, const flo
   }
 }
 
+int g_agg_impl = 2;     // pg_set_option("agg_impl", 1|2|3): 1 = row-per-group kernel, 2 = chunked kernels (need pg_csr::chunks),
+                        // 3 = chunked, long rows staged through shared memory with cp.async
 int g_agg_unroll = 8;   // pg_set_option("agg_unroll", 4|8): neighbour rows in flight per group (VPL == 1, agg_impl 1)
 int g_agg_occ = 4;      // pg_set_option("agg_occ", 4|5): resident CTAs per SM the long-row kernel is compiled for (64 / 48 registers)
 int g_agg_l2_hint = 1; // pg_set_option("agg_l2_hint", 0|1): L2 eviction policies by source hotness in the chunked kernel
@@ -399,6 +415,106 @@ agg2_long_kernel(pg_csr g, const T* __restrict__ x, uint32_t ldx_bytes, T* __res
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// v3 of the long-row kernel: neighbour rows are STAGED THROUGH SHARED MEMORY with asynchronous copies.
+// profiles/r2b_*: the register-landing kernels are bound by latency x bytes in flight -- a load in flight owns its
+// destination registers, and 32 warps x 8 rows x 512 B = 131 KB per SM against ~1.5 us of DRAM-miss latency is
+// ~13 TB/s, where the L2 can feed 20 (tools/gather_micro.cu).  Here every warp owns a ring of D row slots in shared
+// memory; `cp.async` (LDGSTS) moves 16 bytes per lane straight from global memory into the ring, one commit group
+// per row, D - 1 rows ahead of the row being added.  A lane reads back exactly the 16 bytes it copied itself, so the
+// ring needs no barrier at all: `cp.async.wait_group` is the only synchronisation.  (TMA `tile::gather4` into the
+// same kind of ring was measured first: 6.2 TB/s against 20 for plain loads -- profiles/r2_gather_micro.jsonl.)
+__device__ __forceinline__ void cp_async16(uint32_t smem, const void* gmem) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(smem), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async16_policy(uint32_t smem, const void* gmem, uint64_t pol) {
+  asm volatile("cp.async.ca.shared.global.L2::cache_hint [%0], [%1], 16, %2;" ::"r"(smem), "l"(gmem), "l"(pol) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
+template <typename T, int VPL, int D, bool HINT>
+__global__ void __launch_bounds__(256, (VPL == 1 ? 6 : 3))
+agg3_long_kernel(pg_csr g, const T* __restrict__ x, uint32_t ldx_bytes, T* __restrict__ out, int64_t ldo, int nvec,
+                 const float* __restrict__ row_div, int acc_rows, float* __restrict__ scratch, int64_t lds) {
+  using A = Agg2<T, 16, VPL, 1, HINT>;
+  using Raw = typename A::Raw;
+  constexpr int V = A::V;
+  constexpr unsigned kFull = 0xffffffffu;
+  constexpr int kSlotBytes = VPL * 512;
+  extern __shared__ __align__(16) uint8_t agg3_ring[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int cid = blockIdx.x * 8 + warp;
+  if (cid >= g.n_chunks_long) return;
+  const int4 c = __ldcs(reinterpret_cast<const int4*>(g.chunks) + cid);
+  const uint32_t* __restrict__ pidx = reinterpret_cast<const uint32_t*>(g.pidx) + c.x;
+  const int n_e = c.y;
+  // this lane's 16 bytes of slot 0 (piece j at + j * 512)
+  const uint32_t ring = static_cast<uint32_t>(__cvta_generic_to_shared(agg3_ring)) + warp * (D * kSlotBytes) + lane * 16;
+  A a;
+  agg2_setup(a, x, ldx_bytes, out, ldo, acc_rows);
+  if (HINT) {
+    a.pol_hot = l2_policy_evict_last();
+    a.pol_cold = l2_policy_evict_first();
+  }
+  auto issue = [&](int e, uint32_t s) {
+    const uint32_t dst = ring + static_cast<uint32_t>(e & (D - 1)) * kSlotBytes;
+    const uint64_t off = static_cast<uint64_t>(s & 0x7fffffffu) * ldx_bytes;
+#pragma unroll
+    for (int j = 0; j < VPL; ++j) {
+      if (HINT) cp_async16_policy(dst + j * 512, a.xc[j] + off, (s >> 31) ? a.pol_hot : a.pol_cold);
+      else cp_async16(dst + j * 512, a.xc[j] + off);
+    }
+  };
+  for (int c0 = 0; c0 < nvec; c0 += 32 * VPL) {
+    agg2_columns(a, x, c0, lane, nvec);
+    uint32_t idx_a = lane < n_e ? __ldcs(pidx + lane) : 0u;
+    uint32_t idx_b = 32 + lane < n_e ? __ldcs(pidx + 32 + lane) : 0u;
+#pragma unroll
+    for (int k = 0; k < D - 1; ++k) {                       // prologue: rows 0 .. D-2 (all inside the first 32 indices)
+      const uint32_t s = __shfl_sync(kFull, idx_a, k);
+      if (k < n_e) issue(k, s);
+      cp_async_commit();
+    }
+#pragma unroll 1
+    for (int base = 0; base < n_e; base += 32) {
+      const int n = min(32, n_e - base);
+#pragma unroll 4
+      for (int u = 0; u < n; ++u) {
+        const int ui = u + D - 1;                            // position of the row to fetch now, relative to `base`
+        const uint32_t sa = __shfl_sync(kFull, idx_a, ui & 31), sb = __shfl_sync(kFull, idx_b, ui & 31);
+        if (base + ui < n_e) issue(base + ui, ui < 32 ? sa : sb);
+        cp_async_commit();
+        cp_async_wait<D - 1>();                              // row base + u has landed
+        const uint32_t src = ring + static_cast<uint32_t>((base + u) & (D - 1)) * kSlotBytes;
+        Raw v[VPL];
+#pragma unroll
+        for (int j = 0; j < VPL; ++j)
+          asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
+                       : "=r"(v[j].x), "=r"(v[j].y), "=r"(v[j].z), "=r"(v[j].w) : "r"(src + j * 512));
+        a.add(v);
+      }
+      idx_a = idx_b;
+      idx_b = base + 64 + lane < n_e ? __ldcs(pidx + base + 64 + lane) : 0u;
+    }
+    if ((c.w & 3) == 2) {
+      float* sp = scratch + static_cast<int64_t>(c.z) * lds;
+#pragma unroll
+      for (int j = 0; j < VPL; ++j) {
+        if (!a.act[j]) continue;
+        const int64_t o = static_cast<int64_t>(c0 + lane + j * 32) * V;
+#pragma unroll
+        for (int i = 0; i < V; ++i) sp[o + i] = (i & 1) ? a.acc[j][i / 2].y : a.acc[j][i / 2].x;
+      }
+    } else {
+      const int row = __ldg(g.prow + c.z);
+      a.flush(row, row_div != nullptr ? 1.f / __ldg(row_div + row) : 1.f);
+    }
+  }
+}
+
 // chunks [n_chunks_long, n_chunks): n_rows whole rows of equal length (<= 32 entries together) per warp
 template <typename T, int VB, int VPL, int U, bool HINT>
 __global__ void __launch_bounds__(256, (VPL == 1 ? 3 : (VPL == 2 ? 2 : 1)))
@@ -434,7 +550,19 @@ static int launch_agg2h(const pg_csr& g, const T* x, int64_t ldx, T* out, int64_
                         const float* row_div, int acc_rows, float* scratch, int64_t lds, cudaStream_t st) {
   constexpr int U = (VPL >= 4) ? 2 : (VPL == 2 ? 4 : 8);
   const uint32_t ldxb = static_cast<uint32_t>(ldx * sizeof(T));
-  if (g.n_chunks_long > 0) {
+  if (g.n_chunks_long > 0 && g_agg_impl == 3 && VB == 16) {
+    constexpr int D = (VPL >= 4) ? 4 : 8;
+    const unsigned blocks = static_cast<unsigned>((g.n_chunks_long + 7) / 8);
+    const size_t smem = static_cast<size_t>(8) * D * VPL * 512;
+    static bool attr_done = false;
+    if (!attr_done) {
+      PG_CHECK_CUDA(cudaFuncSetAttribute(agg3_long_kernel<T, VPL, D, HINT>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+      PG_CHECK_CUDA(cudaFuncSetAttribute(agg3_long_kernel<T, VPL, D, HINT>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+      attr_done = true;
+    }
+    agg3_long_kernel<T, VPL, D, HINT><<<blocks, 256, smem, st>>>(g, x, ldxb, out, ldo, nvec, row_div, acc_rows, scratch, lds);
+    PG_LAUNCH_CHECK();
+  } else if (g.n_chunks_long > 0) {
     const unsigned blocks = static_cast<unsigned>((g.n_chunks_long + 7) / 8);
     if (VPL == 1 && g_agg_occ == 5)
       agg2_long_kernel<T, VB, VPL, U, HINT, (VPL == 1 ? 5 : 4)><<<blocks, 256, 0, st>>>(g, x, ldxb, out, ldo, nvec, row_div, acc_rows, scratch, lds);
@@ -448,7 +576,7 @@ static int launch_agg2h(const pg_csr& g, const T* x, int64_t ldx, T* out, int64_
     PG_LAUNCH_CHECK();
   }
   if (g.n_long > 0) {
-    agg_fixup_kernel<T, VB><<<g.n_long, 256, 0, st>>>(g, out, ldo, nvec, row_div, acc_rows, scratch, lds);
+    agg_fixup_kernel<T, VB><<<(g.n_long + 7) / 8, 256, 0, st>>>(g, out, ldo, nvec, row_div, acc_rows, scratch, lds);
     PG_LAUNCH_CHECK();
   }
   return PG_OK;
@@ -461,7 +589,6 @@ static int launch_agg2(const pg_csr& g, const T* x, int64_t ldx, T* out, int64_t
   return launch_agg2h<T, VB, VPL, false>(g, x, ldx, out, ldo, nvec, row_div, acc_rows, scratch, lds, st);
 }
 
-int g_agg_impl = 2;     // pg_set_option("agg_impl", 1|2): 1 = row-per-group kernel, 2 = chunked kernel (needs pg_csr::chunks)
 int g_agg_pack_short = 0;   // pg_set_option("agg_pack_short", 0|1): 16 lanes x 2 vectors per row when rows are short.
                             // OFF: measured slower (tools/agg_micro.py, P=8 partition: bwd 277 -> 312 us)
 
@@ -490,7 +617,7 @@ static int launch_agg_u(const pg_csr& g, const T* x, int64_t ldx, T* out, int64_
     PG_LAUNCH_CHECK();
   }
   if (g.n_long > 0) {
-    agg_fixup_kernel<T, VB><<<g.n_long, 256, 0, st>>>(g, out, ldo, nvec, row_div, acc_rows, scratch, lds);
+    agg_fixup_kernel<T, VB><<<(g.n_long + 7) / 8, 256, 0, st>>>(g, out, ldo, nvec, row_div, acc_rows, scratch, lds);
     PG_LAUNCH_CHECK();
   }
   return PG_OK;
@@ -500,7 +627,7 @@ template <typename T, int VB>
 static int dispatch_agg(const pg_csr& g, const T* x, int64_t ldx, T* out, int64_t ldo, int nvec,
                         const float* row_div, int acc_rows, float* scratch, int64_t lds, cudaStream_t st) {
 #define PG_AGG(G_, VPL_) return launch_agg<T, VB, G_, VPL_>(g, x, ldx, out, ldo, nvec, row_div, acc_rows, scratch, lds, st)
-  if (g_agg_impl == 2 && g.chunks != nullptr && nvec > 16) {
+  if (g_agg_impl >= 2 && g.chunks != nullptr && nvec > 16) {
     if (nvec <= 32) return launch_agg2<T, VB, 1>(g, x, ldx, out, ldo, nvec, row_div, acc_rows, scratch, lds, st);
     if (nvec <= 64) return launch_agg2<T, VB, 2>(g, x, ldx, out, ldo, nvec, row_div, acc_rows, scratch, lds, st);
     return launch_agg2<T, VB, 4>(g, x, ldx, out, ldo, nvec, row_div, acc_rows, scratch, lds, st);
@@ -613,7 +740,7 @@ extern "C" int pg_set_option(const char* name, int value) {
     return PG_OK;
   }
   if (strcmp(name, "agg_impl") == 0) {
-    PG_REQUIRE(value == 1 || value == 2, "agg_impl must be 1 or 2");
+    PG_REQUIRE(value >= 1 && value <= 3, "agg_impl must be 1, 2 or 3");
     pg::g_agg_impl = value;
     return PG_OK;
   }

@@ -3,12 +3,14 @@
 //   D[n, k] = sum_s sum_m  G_s[m, n] * X_s[m, k]            n <= 256 outputs, k <= 256 inputs, m = rows (10^5..10^6)
 //
 // i.e. gW1 = g^T feat[:N_in] and gW2 = g^T ah of the autograd of /root/reference/module/layer.py:51 (one call each),
-// with three (G, X) pairs per product for fp32 activations (3xTF32: hi*hi + hi*lo + lo*hi).
+// with three (G, X) pairs per product for fp32 activations (3xTF32: hi*hi + hi*lo + lo*hi), or six bf16 pairs
+// (fp32 = b0 + b1 + b2 in bf16: b0*b0 + b0*b1 + b1*b0 + b0*b2 + b2*b0 + b1*b1).
 //
 // Both operands are row-major [m, .]: the contraction index m is the SLOW index, so the tiles are MN-major for the
 // tensor core (instruction-descriptor bits a_major = b_major = 1).  A TMA box of [128 bytes of n] x [KB rows of m]
 // with the 128-byte swizzle is exactly one column of the canonical MN-major SWIZZLE_128B layout
-// ((8,n),(8,k)):((1,LBO),(8,SBO)) in 16-byte units: SBO = 8 rows * 128 B, LBO = one box.
+// ((8,n),(8,k)):((1,LBO),(8,SBO)) in 16-byte units: SBO = 8 rows * 128 B, LBO = one box (tf32: the 32-byte-atom
+// variant of the swizzle, 4 rows per atom).
 // Split-K over m: every CTA owns a contiguous range of rows, accumulates its partial D in TMEM (two M=128
 // accumulators when n > 128) and writes it to a workspace; a second kernel sums the partials in split order
 // (deterministic).  HBM-bound: every operand row is read once per call.
@@ -21,7 +23,7 @@ namespace pg {
 
 constexpr int kWgThreads = 256;
 constexpr int kWgStages = 3;
-constexpr int kWgMaxSrc = 3;
+constexpr int kWgMaxSrc = 6;
 
 struct WgradMaps {
   CUtensorMap a[kWgMaxSrc];   // G_s: dims {n, m}, box {128 B of n, KB rows}
@@ -42,10 +44,16 @@ struct WgradArgs {
   float* partial;            // [splits][n_acc * 128][k_pad]
 };
 
-// MN-major SWIZZLE_128B descriptor: LBO = bytes between 128-byte MN blocks, SBO = 1024 (8 rows of 128 B)
+// MN-major descriptors, LBO = bytes between 128-byte MN blocks:
+//   16-bit operands: SWIZZLE_128B (layout type 2), atoms of 8 rows of m: SBO = 1024 B
+//   32-bit operands (tf32): SWIZZLE_128B_BASE32B (layout type 1; 32-byte chunks swizzled, Swizzle<2,5,2>), atoms of
+//   4 rows of m: SBO = 512 B -- the layout TMA writes with CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B
+template <bool kTf32>
 __device__ __forceinline__ uint64_t smem_desc_mn_sw128(uint32_t addr, uint32_t lbo_bytes) {
+  constexpr uint64_t sbo = kTf32 ? 512 : 1024;
+  constexpr uint64_t type = kTf32 ? 1 : 2;
   return static_cast<uint64_t>((addr >> 4) & 0x3FFF) | (static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFF) << 16) |
-         (static_cast<uint64_t>(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+         ((sbo >> 4) << 32) | (1ull << 46) | (type << 61);
 }
 
 template <bool kTf32>
@@ -122,9 +130,9 @@ wgrad_tcgen05_kernel(const __grid_constant__ WgradMaps maps, const WgradArgs p) 
         const uint32_t sa = smem_u32(smem + stage * stage_bytes);
         const uint32_t sb = sa + a_bytes;
         for (int ks = 0; ks < p.kb_rows / k_rows; ++ks) {
-          const uint64_t bd = smem_desc_mn_sw128(sb + ks * k_rows * 128, box_bytes);
+          const uint64_t bd = smem_desc_mn_sw128<kTf32>(sb + ks * k_rows * 128, box_bytes);
           for (int acc = 0; acc < p.n_acc; ++acc) {
-            const uint64_t ad = smem_desc_mn_sw128(sa + acc * blocks_per_acc * box_bytes + ks * k_rows * 128, box_bytes);
+            const uint64_t ad = smem_desc_mn_sw128<kTf32>(sa + acc * blocks_per_acc * box_bytes + ks * k_rows * 128, box_bytes);
             tc_mma<kTf32>(tmem_base + static_cast<uint32_t>(acc * 256), ad, bd, p.idesc, (it > 0 || ks > 0) ? 1u : 0u);
           }
         }
@@ -197,7 +205,8 @@ static int make_mn_map(CUtensorMap* map, const void* ptr, int64_t ld, int m, int
   cuuint32_t estr[2] = {1, 1};
   CUresult r = enc(map, tf32 ? CU_TENSOR_MAP_DATA_TYPE_TFLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2,
                    const_cast<void*>(ptr), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                   tf32 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed (%d) m=%d cols=%d ld=%lld", (int)r, m, cols, (long long)ld); return PG_ERR_CUDA; }
   return PG_OK;
 }

@@ -176,6 +176,19 @@ def gemm_nt(a0, b0, a1=None, b1=None, bias=None, row_div=None, out=None, out_dty
 
 
 _WG_WS = {}
+# fp32 weight gradients: "3xtf32" = MN-major kind::tf32 with hi/lo splits, "bf16x3" = six MN-major kind::f16 products
+WGRAD_FP32 = os.environ.get("PG_WGRAD_FP32", "3xtf32")
+
+
+def _split_bf16x3(x: torch.Tensor):
+    out, r = [], x.float()
+    for _ in range(3):
+        b = alloc_rows(x.shape[0], x.shape[1], torch.bfloat16, x.device)
+        b.copy_(r)
+        out.append(b)
+        r = r - b.float()
+    return out
+
 
 
 def wgrad(g: torch.Tensor, x: torch.Tensor) -> torch.Tensor:
@@ -187,12 +200,16 @@ def wgrad(g: torch.Tensor, x: torch.Tensor) -> torch.Tensor:
     out = torch.empty(n, k, dtype=torch.float32, device=g.device)
     if m == 0:
         return out.zero_()
-    if g.dtype == torch.float32 and FP32_GEMM == "3xtf32":
+    if g.dtype == torch.float32 and FP32_GEMM == "3xtf32" and WGRAD_FP32 == "3xtf32":
         (gh, gl), (xh, xl) = split_tf32(g), split_tf32(x)
         pairs = [(gh, xh), (gh, xl), (gl, xh)]
+    elif g.dtype == torch.float32 and FP32_GEMM == "3xtf32":
+        # fp32 = b0 + b1 + b2 exactly (three bf16 terms): six bf16 products carry the product to ~2^-24
+        g3, x3 = _split_bf16x3(g), _split_bf16x3(x)
+        pairs = [(g3[0], x3[0]), (g3[0], x3[1]), (g3[1], x3[0]), (g3[0], x3[2]), (g3[2], x3[0]), (g3[1], x3[1])]
     else:
         pairs = [(_tma_ready(g), _tma_ready(x))]
-    code = _C.dtype_code(g.dtype)
+    code = _C.dtype_code(pairs[0][0].dtype)
     for n0 in range(0, n, 256):
         for k0 in range(0, k, 256):
             nn, kk = min(256, n - n0), min(256, k - k0)
@@ -200,7 +217,7 @@ def wgrad(g: torch.Tensor, x: torch.Tensor) -> torch.Tensor:
             ws = _WG_WS.get(g.device)
             if ws is None or ws.numel() < need:
                 ws = _WG_WS[g.device] = torch.empty(need, dtype=torch.float32, device=g.device)
-            es = g.element_size()
+            es = pairs[0][0].element_size()
             srcs = (_C.pg_gemm_src * len(pairs))(*[
                 _C.pg_gemm_src(a.data_ptr() + n0 * es, a.stride(0), b.data_ptr() + k0 * es, b.stride(0), m)
                 for a, b in pairs])

@@ -2,7 +2,7 @@
 same generator, same degree skew, same feature/hidden widths, same flags, same dtype -- per-layer exchange buffers and
 layer outputs, logits, loss and reduced gradients against the oracle, at the tolerances SURVEY.md §8c states:
 
-    fp32 exchange/aggregate (f_buf)     rtol 3e-5            (sum order only; rows up to 1e4 terms)
+    fp32 exchange (f_buf of layer 0)    rtol 3e-5            (pure exchange / EMA; deeper f_buf carry a GEMM + LayerNorm)
     fp32 layer outputs / logits         rtol 2e-4, atol 2e-4 (3xTF32 tensor-core product vs MKL sgemm)
     fp32 loss                           rel 1e-4
     bf16 per-layer outputs / logits     rtol 2e-2, atol 1e-2 * scale  (scale = max |ref| of the tensor: LayerNorm'd
@@ -33,7 +33,9 @@ def _hooks(trainer):
     for r, eng in enumerate(trainer.engines):
         for i, layer in enumerate(eng.model.layers):
             def hook(mod, inp, out, r=r, i=i):
-                caps[r][i] = ((inp[1] if len(inp) > 1 else inp[0]).detach().float().cpu(), out.detach().float().cpu())
+                # no host synchronisation inside the forward: in the synchronous exchange mode a rank's stream waits
+                # for pushes the host has not launched yet (LocalWorld: one host thread for all ranks)
+                caps[r][i] = ((inp[1] if len(inp) > 1 else inp[0]).detach().clone(), out.detach().clone())
             layer.register_forward_hook(hook)
     return caps
 
@@ -58,7 +60,7 @@ def _run(spec, n_parts, n_epochs, dtype, free_running=False, **flags):
         losses = trainer.run_epoch(keep_logits=True)
         out.append(dict(loss=[float(l.item()) for l in losses],
                         logits=[en.last_logits.float().cpu() for en in trainer.engines],
-                        layers=[dict(c) for c in caps],
+                        layers=[{i: (a.float().cpu(), b.float().cpu()) for i, (a, b) in c.items()} for c in caps],
                         grads=[{n: p.grad.detach().float().cpu().clone() for n, p in en.model.named_parameters()}
                                for en in trainer.engines]))
     return traces, out
@@ -77,7 +79,8 @@ def test_cfg1_reddit_shaped_p2_fp32_per_layer():
     for e, ep in enumerate(out):
         for r in range(2):
             for i, rec in traces[r].layers[e].items():
-                _close(ep["layers"][r][i][0], rec["f_buf"], 3e-5, 1e-6, f"epoch {e} rank {r} f_buf[{i}]")
+                _close(ep["layers"][r][i][0], rec["f_buf"], 3e-5 if i == 0 else 2e-4, 1e-6 if i == 0 else 2e-4,
+                       f"epoch {e} rank {r} f_buf[{i}]")
                 _close(ep["layers"][r][i][1], rec["layer_out"], 2e-4, 2e-4, f"epoch {e} rank {r} layer_out[{i}]")
             _close(ep["logits"][r], traces[r].logits[e], 2e-4, 2e-4, f"epoch {e} rank {r} logits")
             assert abs(ep["loss"][r] - traces[r].losses[e]) <= 1e-4 * abs(traces[r].losses[e])
@@ -92,7 +95,8 @@ def test_cfg2_rmat_fp32_per_layer(n_parts):
     for e, ep in enumerate(out):
         for r in range(n_parts):
             for i, rec in traces[r].layers[e].items():
-                _close(ep["layers"][r][i][0], rec["f_buf"], 3e-5, 1e-6, f"epoch {e} rank {r} f_buf[{i}]")
+                _close(ep["layers"][r][i][0], rec["f_buf"], 3e-5 if i == 0 else 2e-4, 1e-6 if i == 0 else 2e-4,
+                       f"epoch {e} rank {r} f_buf[{i}]")
                 _close(ep["layers"][r][i][1], rec["layer_out"], 2e-4, 2e-4, f"epoch {e} rank {r} layer_out[{i}]")
             _close(ep["logits"][r], traces[r].logits[e], 2e-4, 2e-4, f"epoch {e} rank {r} logits")
             assert abs(ep["loss"][r] - traces[r].losses[e]) <= 1e-4 * abs(traces[r].losses[e])

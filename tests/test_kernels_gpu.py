@@ -253,7 +253,8 @@ def test_dropout_kernel(dtype):
 @pytest.mark.parametrize("d", [100, 256, 602])
 def test_chunked_kernel_equals_row_kernel(dtype, d):
     """agg_impl 2 (chunks of whole short rows / one row / one segment per warp, indices loaded coalesced and
-    broadcast by shuffles) sums every row in the same order as agg_impl 1: bit-identical results, including rows
+    broadcast by shuffles) and agg_impl 3 (long rows staged through shared memory with cp.async) sum every row in
+    the same order as agg_impl 1: bit-identical results, including rows
     without entries, rows longer than the segment length, the division and the accumulate mode."""
     from pipegcn_b200 import _C, ops
     from pipegcn_b200.graph import CsrPlan, alloc_rows
@@ -269,7 +270,7 @@ def test_chunked_kernel_equals_row_kernel(dtype, d):
     base.copy_(torch.randn(n_rows, d, generator=g).to(dtype))
     outs = []
     try:
-        for impl in (1, 2):
+        for impl in (1, 2, 3):
             _C.check(_C.lib.pg_set_option(b"agg_impl", impl))
             o = base.clone()
             o2 = alloc_rows(n_rows, d, dtype, DEV)
@@ -278,7 +279,8 @@ def test_chunked_kernel_equals_row_kernel(dtype, d):
             outs.append((ops.aggregate(plan, x, row_div=div).clone(), o2.clone()))
     finally:
         _C.lib.pg_set_option(b"agg_impl", 2)
-    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
+    for o in outs[1:]:
+        assert torch.equal(outs[0][0], o[0]) and torch.equal(outs[0][1], o[1])
     ref = _ref_agg(indptr, indices, x.float().cpu(), div.cpu())
     tol = 2e-5 if dtype == torch.float32 else 1.6e-2
     assert (outs[1][0].float().cpu().double() - ref).abs().max().item() <= tol * ref.abs().max().item() + 1e-6
@@ -299,6 +301,15 @@ def test_wgrad_matches_torch(dtype, m, n, k):
     x.copy_(torch.randn(m, k, generator=gen).to(dtype))
     out = ops.wgrad(g, x)
     assert out.shape == (n, k) and out.dtype == torch.float32
+    if dtype == torch.float32:          # both fp32 evaluations: MN-major tf32 (3 passes) and bf16 x 3 (6 passes)
+        other = "bf16x3" if ops.WGRAD_FP32 == "3xtf32" else "3xtf32"
+        saved, ops.WGRAD_FP32 = ops.WGRAD_FP32, other
+        try:
+            out2 = ops.wgrad(g, x)
+        finally:
+            ops.WGRAD_FP32 = saved
+        ref2 = g.double().cpu().t() @ x.double().cpu()
+        assert (out2.double().cpu() - ref2).abs().max().item() <= 3e-5 * max(ref2.abs().max().item(), 1.0) + 1e-6, other
     ref = g.double().cpu().t() @ x.double().cpu()
     err = (out.double().cpu() - ref).abs().max().item()
     assert err <= 3e-5 * max(ref.abs().max().item(), 1.0) + 1e-6, (err, ref.abs().max().item())

@@ -1,6 +1,7 @@
 """Aggregate kernel benchmark on one partition of a P-way split of a named shape (what a rank of a P-GPU run executes):
 forward (CSR by destination, with the division) and backward (CSC by source, accumulate) for the kernel variants
-(`agg_impl` 1 = row per lane group; 2 = chunked, with/without L2 eviction hints, compiled for 4 or 5 CTAs per SM),
+(`agg_impl` 1 = row per lane group; 2 = chunked; 3 = chunked with the long rows staged through shared memory by
+cp.async; n/h = without/with L2 eviction hints; 4/5 = CTAs per SM the register-landing long-row kernel is built for),
 CUDA-event timed, checked against cuSPARSE (fp32 SpMM); one JSON line per variant.
 
     python tools/agg_bench.py [shape=rmat-1m] [P=1] [dtype=bf16] [d=n_feat] [--once] [--variants 1,2h4,...]
@@ -20,7 +21,7 @@ from pipegcn_b200.synthetic import make_graph, random_partition
 
 argv = [a for a in sys.argv[1:] if not a.startswith("--")]
 once = "--once" in sys.argv
-variants = ["1", "2n4", "2h4", "2n5", "2h5"]
+variants = ["1", "2n4", "2h4", "3n4", "3h4"]
 if "--variants" in sys.argv:
     variants = sys.argv[sys.argv.index("--variants") + 1].split(",")
     argv = [a for a in argv if a != ",".join(variants)]
@@ -72,7 +73,7 @@ def timeit(fn, n=20):
 for var in variants:
     impl = int(var[0])
     _C.check(_C.lib.pg_set_option(b"agg_impl", impl))
-    if impl == 2:
+    if impl >= 2:
         _C.check(_C.lib.pg_set_option(b"agg_l2_hint", 1 if var[1] == "h" else 0))
         _C.check(_C.lib.pg_set_option(b"agg_occ", int(var[2])))
     of = ops.aggregate(graph.fwd, x, row_div=graph.in_deg_f)
