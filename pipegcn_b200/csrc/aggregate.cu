@@ -124,53 +124,69 @@ agg_kernel(pg_csr g, const T* __restrict__ x, uint32_t ldx_bytes, T* __restrict_
   }
 }
 
-// sums the fp32 partials of every long row in segment order and writes the row: one warp per long row, four
-// partials in flight
+// sums the fp32 partials of every long row and writes the row: one CTA per long row, warp w adds the segments
+// s0 + w, s0 + w + 8, ... (four in flight), then the eight warp sums are added in warp order -- a fixed order, so the
+// result does not depend on scheduling
 template <typename T, int VB>
 __global__ void __launch_bounds__(256)
 agg_fixup_kernel(pg_csr g, T* __restrict__ out, int64_t ldo, int nvec, const float* __restrict__ row_div,
                  int acc_rows, const float* __restrict__ scratch, int64_t lds) {
   using P = Pack<T, VB>;
   constexpr int V = P::V;
-  const int li = blockIdx.x * 8 + (threadIdx.x >> 5);
-  if (li >= g.n_long) return;
-  const int lane = threadIdx.x & 31;
+  __shared__ float part[8][32 * V];
+  const int li = blockIdx.x;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int row = __ldg(g.long_row + li);
   const int s0 = __ldg(g.long_seg_ptr + li), s1 = __ldg(g.long_seg_ptr + li + 1);
   const float inv = row_div ? 1.f / __ldg(row_div + row) : 1.f;
   T* op = out + static_cast<int64_t>(row) * ldo;
-  for (int vi = lane; vi < nvec; vi += 32) {
+  for (int v0 = 0; v0 < nvec; v0 += 32) {
+    const int vi = v0 + lane;
     float r[V];
 #pragma unroll
     for (int i = 0; i < V; ++i) r[i] = 0.f;
-    const float* sp = scratch + static_cast<int64_t>(vi) * V;
-    int s = s0;
-    for (; s + 4 <= s1; s += 4) {
-      float t[4][V];
+    if (vi < nvec) {
+      const float* sp = scratch + static_cast<int64_t>(vi) * V;
+      int s = s0 + warp;
+      for (; s + 24 < s1; s += 32) {
+        float t[4][V];
 #pragma unroll
-      for (int u = 0; u < 4; ++u)
+        for (int u = 0; u < 4; ++u)
 #pragma unroll
-        for (int i = 0; i < V; ++i) t[u][i] = __ldcs(sp + static_cast<int64_t>(s + u) * lds + i);
+          for (int i = 0; i < V; ++i) t[u][i] = __ldcs(sp + static_cast<int64_t>(s + 8 * u) * lds + i);
 #pragma unroll
-      for (int u = 0; u < 4; ++u)
+        for (int u = 0; u < 4; ++u)
 #pragma unroll
-        for (int i = 0; i < V; ++i) r[i] += t[u][i];
+          for (int i = 0; i < V; ++i) r[i] += t[u][i];
+      }
+      for (; s < s1; s += 8)
+#pragma unroll
+        for (int i = 0; i < V; ++i) r[i] += __ldcs(sp + static_cast<int64_t>(s) * lds + i);
     }
-    for (; s < s1; ++s)
 #pragma unroll
-      for (int i = 0; i < V; ++i) r[i] += __ldcs(sp + static_cast<int64_t>(s) * lds + i);
+    for (int i = 0; i < V; ++i) part[warp][lane * V + i] = r[i];
+    __syncthreads();
+    if (warp == 0 && vi < nvec) {
 #pragma unroll
-    for (int i = 0; i < V; ++i) r[i] *= inv;
-    if (row < acc_rows) {
-      float o[V];
-      P::unpack(*reinterpret_cast<const typename P::Raw*>(op + static_cast<int64_t>(vi) * V), o);
+      for (int i = 0; i < V; ++i) {
+        float a = part[0][lane * V + i];
 #pragma unroll
-      for (int i = 0; i < V; ++i) r[i] += o[i];
+        for (int w = 1; w < 8; ++w) a += part[w][lane * V + i];
+        r[i] = a * inv;
+      }
+      if (row < acc_rows) {
+        float o[V];
+        P::unpack(*reinterpret_cast<const typename P::Raw*>(op + static_cast<int64_t>(vi) * V), o);
+#pragma unroll
+        for (int i = 0; i < V; ++i) r[i] += o[i];
+      }
+      st_vec<VB>(op + static_cast<int64_t>(vi) * V, P::pack(r));
     }
-    st_vec<VB>(op + static_cast<int64_t>(vi) * V, P::pack(r));
+    __syncthreads();
   }
 }
 
+int g_agg_overlap = 1; // pg_set_option("agg_overlap", 0|1): short-row kernel on a side stream next to the long-row kernel
 int g_agg_impl = 2;     // pg_set_option("agg_impl", 1|2|3): 1 = row-per-group kernel, 2 = chunked kernels (need pg_csr::chunks),
                         // 3 = chunked, long rows staged through shared memory with cp.async
 int g_agg_unroll = 8;   // pg_set_option("agg_unroll", 4|8): neighbour rows in flight per group (VPL == 1, agg_impl 1)
@@ -517,7 +533,7 @@ agg3_long_kernel(pg_csr g, const T* __restrict__ x, uint32_t ldx_bytes, T* __res
 
 // chunks [n_chunks_long, n_chunks): n_rows whole rows of equal length (<= 32 entries together) per warp
 template <typename T, int VB, int VPL, int U, bool HINT>
-__global__ void __launch_bounds__(256, (VPL == 1 ? 3 : (VPL == 2 ? 2 : 1)))
+__global__ void __launch_bounds__(256, (VPL == 1 ? 4 : (VPL == 2 ? 2 : 1)))
 agg2_small_kernel(pg_csr g, const T* __restrict__ x, uint32_t ldx_bytes, T* __restrict__ out, int64_t ldo, int nvec,
                   const float* __restrict__ row_div, int acc_rows) {
   using A = Agg2<T, VB, VPL, U, HINT>;
@@ -545,11 +561,46 @@ agg2_small_kernel(pg_csr g, const T* __restrict__ x, uint32_t ldx_bytes, T* __re
   }
 }
 
+// The long-row kernel is bound by instruction issue and L2 bandwidth, the short-row kernel by DRAM latency (it
+// touches the cold sources and writes most of the output): they run side by side, the short rows on a side stream
+// forked from and joined to the caller's stream with events (legal inside a CUDA-graph capture).
+struct AggSide { cudaStream_t main; cudaStream_t side; cudaEvent_t fork, join; };
+static AggSide g_agg_side[32];
+static int g_agg_n_side = 0;
+static AggSide* agg_side_for(cudaStream_t st) {
+  for (int i = 0; i < g_agg_n_side; ++i)
+    if (g_agg_side[i].main == st) return &g_agg_side[i];
+  if (g_agg_n_side == 32) return nullptr;
+  AggSide& e = g_agg_side[g_agg_n_side];
+  e.main = st;
+  if (cudaStreamCreateWithFlags(&e.side, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaEventCreateWithFlags(&e.fork, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&e.join, cudaEventDisableTiming) != cudaSuccess) {
+    cudaGetLastError();
+    return nullptr;
+  }
+  ++g_agg_n_side;
+  return &e;
+}
+
 template <typename T, int VB, int VPL, bool HINT>
 static int launch_agg2h(const pg_csr& g, const T* x, int64_t ldx, T* out, int64_t ldo, int nvec,
                         const float* row_div, int acc_rows, float* scratch, int64_t lds, cudaStream_t st) {
   constexpr int U = (VPL >= 4) ? 2 : (VPL == 2 ? 4 : 8);
   const uint32_t ldxb = static_cast<uint32_t>(ldx * sizeof(T));
+  AggSide* side = nullptr;
+  if (g.n_chunks > g.n_chunks_long) {                     // the short rows first, on the side stream if there is other work
+    const unsigned blocks = static_cast<unsigned>((g.n_chunks - g.n_chunks_long + 7) / 8);
+    cudaStream_t ss = st;
+    if (g_agg_overlap && g.n_chunks_long > 0 && (side = agg_side_for(st)) != nullptr) {
+      PG_CHECK_CUDA(cudaEventRecord(side->fork, st));
+      PG_CHECK_CUDA(cudaStreamWaitEvent(side->side, side->fork, 0));
+      ss = side->side;
+    }
+    agg2_small_kernel<T, VB, VPL, U, HINT><<<blocks, 256, 0, ss>>>(g, x, ldxb, out, ldo, nvec, row_div, acc_rows);
+    PG_LAUNCH_CHECK();
+    if (side != nullptr) PG_CHECK_CUDA(cudaEventRecord(side->join, ss));
+  }
   if (g.n_chunks_long > 0 && g_agg_impl == 3 && VB == 16) {
     constexpr int D = (VPL >= 4) ? 4 : 8;
     const unsigned blocks = static_cast<unsigned>((g.n_chunks_long + 7) / 8);
@@ -570,15 +621,11 @@ static int launch_agg2h(const pg_csr& g, const T* x, int64_t ldx, T* out, int64_
       agg2_long_kernel<T, VB, VPL, U, HINT, 4><<<blocks, 256, 0, st>>>(g, x, ldxb, out, ldo, nvec, row_div, acc_rows, scratch, lds);
     PG_LAUNCH_CHECK();
   }
-  if (g.n_chunks > g.n_chunks_long) {
-    const unsigned blocks = static_cast<unsigned>((g.n_chunks - g.n_chunks_long + 7) / 8);
-    agg2_small_kernel<T, VB, VPL, U, HINT><<<blocks, 256, 0, st>>>(g, x, ldxb, out, ldo, nvec, row_div, acc_rows);
-    PG_LAUNCH_CHECK();
-  }
   if (g.n_long > 0) {
-    agg_fixup_kernel<T, VB><<<(g.n_long + 7) / 8, 256, 0, st>>>(g, out, ldo, nvec, row_div, acc_rows, scratch, lds);
+    agg_fixup_kernel<T, VB><<<g.n_long, 256, 0, st>>>(g, out, ldo, nvec, row_div, acc_rows, scratch, lds);
     PG_LAUNCH_CHECK();
   }
+  if (side != nullptr) PG_CHECK_CUDA(cudaStreamWaitEvent(st, side->join, 0));
   return PG_OK;
 }
 
@@ -617,7 +664,7 @@ static int launch_agg_u(const pg_csr& g, const T* x, int64_t ldx, T* out, int64_
     PG_LAUNCH_CHECK();
   }
   if (g.n_long > 0) {
-    agg_fixup_kernel<T, VB><<<(g.n_long + 7) / 8, 256, 0, st>>>(g, out, ldo, nvec, row_div, acc_rows, scratch, lds);
+    agg_fixup_kernel<T, VB><<<g.n_long, 256, 0, st>>>(g, out, ldo, nvec, row_div, acc_rows, scratch, lds);
     PG_LAUNCH_CHECK();
   }
   return PG_OK;
@@ -728,6 +775,10 @@ extern "C" int pg_set_option(const char* name, int value) {
   if (strcmp(name, "agg_unroll") == 0) {
     PG_REQUIRE(value == 4 || value == 8, "agg_unroll must be 4 or 8");
     pg::g_agg_unroll = value;
+    return PG_OK;
+  }
+  if (strcmp(name, "agg_overlap") == 0) {
+    pg::g_agg_overlap = value ? 1 : 0;
     return PG_OK;
   }
   if (strcmp(name, "agg_occ") == 0) {

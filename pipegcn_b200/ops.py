@@ -175,7 +175,6 @@ def gemm_nt(a0, b0, a1=None, b1=None, bias=None, row_div=None, out=None, out_dty
     return out
 
 
-_WG_WS = {}
 # fp32 weight gradients: "3xtf32" = MN-major kind::tf32 with hi/lo splits, "bf16x3" = six MN-major kind::f16 products
 WGRAD_FP32 = os.environ.get("PG_WGRAD_FP32", "3xtf32")
 
@@ -213,10 +212,9 @@ def wgrad(g: torch.Tensor, x: torch.Tensor) -> torch.Tensor:
     for n0 in range(0, n, 256):
         for k0 in range(0, k, 256):
             nn, kk = min(256, n - n0), min(256, k - k0)
-            need = int(_C.lib.pg_wgrad_workspace(m, nn, kk, code))
-            ws = _WG_WS.get(g.device)
-            if ws is None or ws.numel() < need:
-                ws = _WG_WS[g.device] = torch.empty(need, dtype=torch.float32, device=g.device)
+            # split-K partials: a fresh block per call (the caching allocator is stream-aware; several simulated
+            # ranks run on their own streams in one process and must not share scratch)
+            ws = torch.empty(int(_C.lib.pg_wgrad_workspace(m, nn, kk, code)), dtype=torch.float32, device=g.device)
             es = pairs[0][0].element_size()
             srcs = (_C.pg_gemm_src * len(pairs))(*[
                 _C.pg_gemm_src(a.data_ptr() + n0 * es, a.stride(0), b.data_ptr() + k0 * es, b.stride(0), m)
@@ -301,7 +299,65 @@ class SageLayerFn(torch.autograd.Function):
         return g_feat, None, None, gw1, gb, gw2, gb
 
 
+class SageLayerNarrowFn(torch.autograd.Function):
+    """The same function as `SageLayerFn`, evaluated TRANSFORM-FIRST when the layer narrows (d_out < d_in):
+
+        z   = feat @ W2^T                          [num_all, d_out]   pg_linear over all rows (inner + halo)
+        out = feat[:N_in] @ W1^T + (b1 + b2)       [N_in, d_out]      pg_linear
+        out += (A @ z) / in_deg                                       pg_aggregate, accumulating, division fused
+
+    (A F) W = A (F W): the aggregate -- the HBM/L2-bound part of /root/reference/module/layer.py:47-51 -- moves
+    d_out-wide rows instead of d_in-wide ones (4x fewer bytes for the 256 -> 64 output layer of the headline config).
+    Backward: dz = A^T (g / in_deg) [num_all, d_out], g_feat = dz @ W2 (+ g @ W1 on the inner rows),
+    gW2 = dz^T feat, gW1 = g^T feat[:N_in].  Same sums, different association: fp32 results agree with the
+    aggregate-first form to rounding (parity tests compare against the oracle, which aggregates first).
+    """
+
+    @staticmethod
+    def forward(ctx, feat, graph, deg_f, w1, b1, w2, b2):
+        if feat.stride(1) != 1:
+            feat = feat.contiguous()
+        n_in = graph.num_in
+        z = gemm_nt(feat, padded_weight(w2, feat.dtype))
+        bias = None
+        if b1 is not None:
+            bias = b1.detach().float() + b2.detach().float()
+        out = gemm_nt(feat[:n_in], padded_weight(w1, feat.dtype), bias=bias)
+        aggregate(graph.fwd, z, out=out, row_div=deg_f, acc_rows=n_in)
+        ctx.graph, ctx.deg_f = graph, deg_f
+        ctx.has_bias = b1 is not None
+        ctx.save_for_backward(feat, w1, w2)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        feat, w1, w2 = ctx.saved_tensors
+        graph, deg_f = ctx.graph, ctx.deg_f
+        n_in = graph.num_in
+        colsum = _take_colsum(g)
+        g = _tma_ready(g if g.dtype == feat.dtype else g.to(feat.dtype))
+        gs = row_div(g, deg_f)
+        dz = aggregate(graph.bwd, gs)                                   # [num_all, d_out]
+        g_feat = None
+        if ctx.needs_input_grad[0]:
+            g_feat = alloc_rows(feat.shape[0], feat.shape[1], feat.dtype, feat.device)
+            w1t, w2t = padded_weight(w1, feat.dtype, transpose=True), padded_weight(w2, feat.dtype, transpose=True)
+            gemm_nt(dz[:n_in], w2t, g, w1t, out=g_feat[:n_in])
+            if feat.shape[0] > n_in:
+                gemm_nt(dz[n_in:], w2t, out=g_feat[n_in:])
+        gw1 = wgrad(g, feat[:n_in]).to(w1.dtype)
+        gw2 = wgrad(dz, feat).to(w2.dtype)
+        gb = (colsum if colsum is not None else g.float().sum(0)) if ctx.has_bias else None
+        return g_feat, None, None, gw1, gb, gw2, gb
+
+
+# transform-first when the layer narrows (PG_NARROW=0 keeps the reference's aggregate-first association everywhere)
+NARROW = os.environ.get("PG_NARROW", "1") != "0"
+
+
 def sage_layer(feat, graph, deg_f, w1, b1, w2, b2) -> torch.Tensor:
+    if NARROW and w1.shape[0] < feat.shape[1]:
+        return SageLayerNarrowFn.apply(feat, graph, deg_f, w1, b1, w2, b2)
     return SageLayerFn.apply(feat, graph, deg_f, w1, b1, w2, b2)
 
 

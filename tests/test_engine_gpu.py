@@ -91,11 +91,18 @@ def test_exposed_comm_timer_sections():
     from tests.helpers import make_args, small_world
     g, _, layouts, _ = small_world("tiny", 2)
     _, eargs = make_args(g, 5)
+    eargs.static_layer0 = False
     trainer = LocalTrainer(layouts, eargs, LocalWorld(2, "cuda"))
     trainer.run_epoch()
     torch.cuda.synchronize()
     sec = trainer.engines[0].buffer.timer.sections()
     assert set(sec) == {"forward_0", "forward_1", "forward_2", "backward_1", "backward_2"}
+    # with the static-layer-0 shortcut (default) layer 0 is exchanged once at set-up: no per-epoch wait
+    _, eargs = make_args(g, 5)
+    trainer2 = LocalTrainer(layouts, eargs, LocalWorld(2, "cuda"))
+    trainer2.run_epoch()
+    torch.cuda.synchronize()
+    assert set(trainer2.engines[0].buffer.timer.sections()) == {"forward_1", "forward_2", "backward_1", "backward_2"}
     assert all(v >= 0 for v in sec.values())
     with pytest.raises(Exception):
         trainer.engines[0].buffer.timer.add_events("forward_0", None, None)   # duplicate name, as the reference

@@ -1,7 +1,8 @@
 """Aggregate kernel benchmark on one partition of a P-way split of a named shape (what a rank of a P-GPU run executes):
 forward (CSR by destination, with the division) and backward (CSC by source, accumulate) for the kernel variants
 (`agg_impl` 1 = row per lane group; 2 = chunked; 3 = chunked with the long rows staged through shared memory by
-cp.async; n/h = without/with L2 eviction hints; 4/5 = CTAs per SM the register-landing long-row kernel is built for),
+cp.async; n/h = without/with L2 eviction hints; 4/5 = CTAs per SM the register-landing long-row kernel is built for;
+trailing s = short-row kernel serialised after the long-row kernel instead of on a side stream),
 CUDA-event timed, checked against cuSPARSE (fp32 SpMM); one JSON line per variant.
 
     python tools/agg_bench.py [shape=rmat-1m] [P=1] [dtype=bf16] [d=n_feat] [--once] [--variants 1,2h4,...]
@@ -21,7 +22,7 @@ from pipegcn_b200.synthetic import make_graph, random_partition
 
 argv = [a for a in sys.argv[1:] if not a.startswith("--")]
 once = "--once" in sys.argv
-variants = ["1", "2n4", "2h4", "3n4", "3h4"]
+variants = ["1", "2n4s", "2h4s", "2n4", "2h4"]
 if "--variants" in sys.argv:
     variants = sys.argv[sys.argv.index("--variants") + 1].split(",")
     argv = [a for a in argv if a != ",".join(variants)]
@@ -76,6 +77,7 @@ for var in variants:
     if impl >= 2:
         _C.check(_C.lib.pg_set_option(b"agg_l2_hint", 1 if var[1] == "h" else 0))
         _C.check(_C.lib.pg_set_option(b"agg_occ", int(var[2])))
+        _C.check(_C.lib.pg_set_option(b"agg_overlap", 0 if var.endswith("s") else 1))
     of = ops.aggregate(graph.fwd, x, row_div=graph.in_deg_f)
     ob = ops.aggregate(graph.bwd, gy, out=torch.zeros_like(gx), acc_rows=0)
     err_f = ((of.float() - ref_f).abs().max() / ref_f.abs().max()).item()
