@@ -191,7 +191,9 @@ int g_agg_impl = 2;     // pg_set_option("agg_impl", 1|2|3): 1 = row-per-group k
                         // 3 = chunked, long rows staged through shared memory with cp.async
 int g_agg_unroll = 8;   // pg_set_option("agg_unroll", 4|8): neighbour rows in flight per group (VPL == 1, agg_impl 1)
 int g_agg_occ = 4;      // pg_set_option("agg_occ", 4|5): resident CTAs per SM the long-row kernel is compiled for (64 / 48 registers)
-int g_agg_l2_hint = 1; // pg_set_option("agg_l2_hint", 0|1): L2 eviction policies by source hotness in the chunked kernel
+int g_agg_l2_hint = 0; // pg_set_option("agg_l2_hint", 0|1): L2 eviction policies by source hotness in the chunked kernels.
+                       // OFF: the policy select costs 5 of 23 instructions per edge on an issue-bound kernel and bought -3 % / +4 %
+                       // (rmat-1m at 1 / 8 partitions) and -2 % (Reddit-shaped): profiles/r2d_agg_bench_*.jsonl
 
 // ---------------------------------------------------------------------------------------------------------
 // v2: chunked walk over the degree-sorted, permuted CSR (pg_csr::chunks / pidx / prow).

@@ -91,5 +91,6 @@ for var in variants:
                           fwd_ms=tf, bwd_ms=tb, fwd_frac_of_6572=bf / tf / 1e6 / 6572.2, bwd_frac_of_6572=bb / tb / 1e6 / 6572.2,
                           fwd_gather_tbs=lay.nnz * d * es / tf / 1e9, bwd_gather_tbs=lay.nnz * d * es / tb / 1e9)), flush=True)
 _C.lib.pg_set_option(b"agg_impl", 2)
-_C.lib.pg_set_option(b"agg_l2_hint", 1)
+_C.lib.pg_set_option(b"agg_l2_hint", 0)
 _C.lib.pg_set_option(b"agg_occ", 4)
+_C.lib.pg_set_option(b"agg_overlap", 1)
