@@ -58,6 +58,8 @@ SHAPES = {
     "reddit-shaped": dict(n_nodes=233_000, n_edges=115_000_000, n_feat=602, n_class=41, train_frac=0.66),
     # configs[3]
     "products-shaped": dict(n_nodes=2_400_000, n_edges=62_000_000, n_feat=100, n_class=47, train_frac=0.08),
+    # configs[4]: built per rank (pipegcn_b200/distgraph.py), never as one global edge list
+    "papers100m-shaped": dict(n_nodes=111_000_000, n_edges=1_600_000_000, n_feat=128, n_class=172, train_frac=0.011),
     # small shapes for tests / smoke
     "tiny": dict(n_nodes=300, n_edges=3_000, n_feat=20, n_class=5, train_frac=0.66),
     "small": dict(n_nodes=20_000, n_edges=400_000, n_feat=64, n_class=16, train_frac=0.66),
