@@ -132,17 +132,48 @@ def split_tf32(x: torch.Tensor):
 FP32_GEMM = os.environ.get("PG_FP32_GEMM", "3xtf32")
 
 
+class Split:
+    """An fp32 operand together with its tf32 (hi, lo) halves, so that one split serves every product that uses the
+    operand (a gradient feeds two dX GEMMs and two weight-gradient GEMMs)."""
+
+    def __init__(self, x: torch.Tensor):
+        self.x = _rows(x)
+        self.hi, self.lo = split_tf32(x)
+
+    def rows(self, lo: int, hi: int = None) -> "Split":
+        out = Split.__new__(Split)
+        out.x, out.hi, out.lo = self.x[lo:hi], self.hi[lo:hi], self.lo[lo:hi]
+        return out
+
+
+def presplit(x: torch.Tensor):
+    """`Split(x)` when x is an fp32 operand of the 3xTF32 product, else x itself."""
+    if isinstance(x, torch.Tensor) and x.dtype == torch.float32 and FP32_GEMM == "3xtf32":
+        return Split(x)
+    return x
+
+
+def _plain(t):
+    return t.x if isinstance(t, Split) else t
+
+
+def _halves(t):
+    return (t.hi, t.lo) if isinstance(t, Split) else split_tf32(t)
+
+
 def gemm_nt(a0, b0, a1=None, b1=None, bias=None, row_div=None, out=None, out_dtype=None) -> torch.Tensor:
-    """out[m, n] = a0 @ b0^T (+ a1 @ b1^T) (+ bias) (/ row_div[:, None]) on the tcgen05 tensor cores."""
-    pairs = [(_rows(a0), _rows(b0))]
-    if a1 is not None:
-        pairs.append((_rows(a1), _rows(b1)))
+    """out[m, n] = a0 @ b0^T (+ a1 @ b1^T) (+ bias) (/ row_div[:, None]) on the tcgen05 tensor cores.  Operands may be
+    `Split` objects (fp32 operands split once by the caller)."""
+    raw = [(a0, b0)] + ([(a1, b1)] if a1 is not None else [])
+    a0, b0 = _plain(a0), _plain(b0)
+    pairs = [(_rows(_plain(a)), _rows(_plain(b))) for a, b in raw]
     m, n = a0.shape[0], b0.shape[0]
     for a, b in pairs:
         assert a.shape[0] == m and b.shape[0] == n and a.shape[1] == b.shape[1] and a.dtype == b.dtype == a0.dtype
     if n > 256:
         # one N tile holds at most 256 columns: split the weight rows
-        outs = [gemm_nt(a0, b0[i:i + 256], a1, None if b1 is None else b1[i:i + 256],
+        outs = [gemm_nt(raw[0][0], b0[i:i + 256], raw[1][0] if len(raw) > 1 else None,
+                        None if len(raw) == 1 else _plain(raw[1][1])[i:i + 256],
                         None if bias is None else bias[i:i + 256], row_div, None, out_dtype)
                 for i in range(0, n, 256)]
         res = torch.cat(outs, dim=1)
@@ -157,8 +188,8 @@ def gemm_nt(a0, b0, a1=None, b1=None, bias=None, row_div=None, out=None, out_dty
         return out
     if a0.dtype == torch.float32 and FP32_GEMM == "3xtf32":
         split = []
-        for a, b in pairs:
-            (ah, al), (bh, bl) = split_tf32(a), split_tf32(b)
+        for a, b in raw:
+            (ah, al), (bh, bl) = _halves(a), _halves(b)
             split += [(ah, bh), (ah, bl), (al, bh)]
         pairs = split
     else:
@@ -193,14 +224,15 @@ def _split_bf16x3(x: torch.Tensor):
 def wgrad(g: torch.Tensor, x: torch.Tensor) -> torch.Tensor:
     """g^T @ x  -> fp32 [n, k]: the weight gradient of `x @ W^T` on the tcgen05 tensor cores (pg_wgrad: MN-major
     operands straight from the row-major activations, split-K over the rows, fixed-order reduction)."""
-    _rows(g), _rows(x)
+    gs, xs = g, x
+    g, x = _rows(_plain(g)), _rows(_plain(x))
     m, n, k = g.shape[0], g.shape[1], x.shape[1]
     assert x.shape[0] == m and g.dtype == x.dtype
     out = torch.empty(n, k, dtype=torch.float32, device=g.device)
     if m == 0:
         return out.zero_()
     if g.dtype == torch.float32 and FP32_GEMM == "3xtf32" and WGRAD_FP32 == "3xtf32":
-        (gh, gl), (xh, xl) = split_tf32(g), split_tf32(x)
+        (gh, gl), (xh, xl) = _halves(gs), _halves(xs)
         pairs = [(gh, xh), (gh, xl), (gl, xh)]
     elif g.dtype == torch.float32 and FP32_GEMM == "3xtf32":
         # fp32 = b0 + b1 + b2 exactly (three bf16 terms): six bf16 products carry the product to ~2^-24
@@ -241,8 +273,9 @@ class _Linear(torch.autograd.Function):
         x, weight = ctx.saved_tensors
         colsum = _take_colsum(g)
         g = _tma_ready(g if g.dtype == x.dtype else g.to(x.dtype))
-        gx = gemm_nt(g, padded_weight(weight, x.dtype, transpose=True)) if ctx.needs_input_grad[0] else None
-        gw = wgrad(g, x).to(weight.dtype)
+        gsp = presplit(g)
+        gx = gemm_nt(gsp, padded_weight(weight, x.dtype, transpose=True)) if ctx.needs_input_grad[0] else None
+        gw = wgrad(gsp, x).to(weight.dtype)
         gb = (colsum if colsum is not None else g.float().sum(0)) if ctx.has_bias else None
         return gx, gw, gb
 
@@ -286,15 +319,16 @@ class SageLayerFn(torch.autograd.Function):
         graph, deg_f = ctx.graph, ctx.deg_f
         colsum = _take_colsum(g)
         g = _tma_ready(g if g.dtype == x.dtype else g.to(x.dtype))
+        gsp = presplit(g)                      # fp32: one split of g serves the two dX and the two dW products
         g_feat = None
         if ctx.needs_input_grad[0]:
             d_in = x.shape[1]
             g_feat = alloc_rows(ctx.num_all, d_in, x.dtype, x.device)
-            gemm_nt(g, padded_weight(w1, x.dtype, transpose=True), out=g_feat[:graph.num_in])
-            gs = gemm_nt(g, padded_weight(w2, x.dtype, transpose=True), row_div=deg_f)
+            gemm_nt(gsp, padded_weight(w1, x.dtype, transpose=True), out=g_feat[:graph.num_in])
+            gs = gemm_nt(gsp, padded_weight(w2, x.dtype, transpose=True), row_div=deg_f)
             aggregate(graph.bwd, gs, out=g_feat, acc_rows=graph.num_in)
-        gw1 = wgrad(g, x).to(w1.dtype)
-        gw2 = wgrad(g, ah).to(w2.dtype)
+        gw1 = wgrad(gsp, x).to(w1.dtype)
+        gw2 = wgrad(gsp, ah).to(w2.dtype)
         gb = (colsum if colsum is not None else g.float().sum(0)) if ctx.has_bias else None
         return g_feat, None, None, gw1, gb, gw2, gb
 
@@ -318,11 +352,12 @@ class SageLayerNarrowFn(torch.autograd.Function):
         if feat.stride(1) != 1:
             feat = feat.contiguous()
         n_in = graph.num_in
-        z = gemm_nt(feat, padded_weight(w2, feat.dtype))
+        fsp = presplit(feat)                   # fp32: one split of feat for both products
+        z = gemm_nt(fsp, padded_weight(w2, feat.dtype))
         bias = None
         if b1 is not None:
             bias = b1.detach().float() + b2.detach().float()
-        out = gemm_nt(feat[:n_in], padded_weight(w1, feat.dtype), bias=bias)
+        out = gemm_nt(fsp.rows(0, n_in) if isinstance(fsp, Split) else feat[:n_in], padded_weight(w1, feat.dtype), bias=bias)
         aggregate(graph.fwd, z, out=out, row_div=deg_f, acc_rows=n_in)
         ctx.graph, ctx.deg_f = graph, deg_f
         ctx.has_bias = b1 is not None
@@ -338,15 +373,17 @@ class SageLayerNarrowFn(torch.autograd.Function):
         g = _tma_ready(g if g.dtype == feat.dtype else g.to(feat.dtype))
         gs = row_div(g, deg_f)
         dz = aggregate(graph.bwd, gs)                                   # [num_all, d_out]
+        gsp, dzsp, fsp = presplit(g), presplit(dz), presplit(feat)
+        is_split = isinstance(fsp, Split)
         g_feat = None
         if ctx.needs_input_grad[0]:
             g_feat = alloc_rows(feat.shape[0], feat.shape[1], feat.dtype, feat.device)
             w1t, w2t = padded_weight(w1, feat.dtype, transpose=True), padded_weight(w2, feat.dtype, transpose=True)
-            gemm_nt(dz[:n_in], w2t, g, w1t, out=g_feat[:n_in])
+            gemm_nt(dzsp.rows(0, n_in) if is_split else dz[:n_in], w2t, gsp, w1t, out=g_feat[:n_in])
             if feat.shape[0] > n_in:
-                gemm_nt(dz[n_in:], w2t, out=g_feat[n_in:])
-        gw1 = wgrad(g, feat[:n_in]).to(w1.dtype)
-        gw2 = wgrad(dz, feat).to(w2.dtype)
+                gemm_nt(dzsp.rows(n_in) if is_split else dz[n_in:], w2t, out=g_feat[n_in:])
+        gw1 = wgrad(gsp, fsp.rows(0, n_in) if is_split else feat[:n_in]).to(w1.dtype)
+        gw2 = wgrad(dzsp, fsp).to(w2.dtype)
         gb = (colsum if colsum is not None else g.float().sum(0)) if ctx.has_bias else None
         return g_feat, None, None, gw1, gb, gw2, gb
 

@@ -188,7 +188,9 @@ class RankEngine:
             self.buffer.load_inner(0, feat.to(self.device, non_blocking=True) if not feat.is_cuda else feat)
             self.static0()          # new features: their halo rows have to be exchanged again
             return
-        self.feat.copy_(feat, non_blocking=True)
+        # --use-pp: `self.feat` is cat(feat, neighbour mean) (train.py:169-189); the raw half is refreshed, the mean is
+        # set-up work of the reference (precompute runs once, train.py:287-288) and is not recomputed per step
+        self.feat[:, :feat.shape[1]].copy_(feat, non_blocking=True)
 
     def finish_epoch(self, reduce=True):
         """train.py:357-362."""
