@@ -77,6 +77,20 @@ typedef struct pg_csr {
 } pg_csr;
 
 /*
+ * Dropout (model.py:47) without a stored mask: keep(element) is a pure function of (seed, step, element index), where
+ * step = *step_dev + step_off is an epoch counter that lives on the device (CUDA-graph replay).  Every kernel that
+ * writes a tensor the next layer consumes can apply it on the way out, so no [num_all, d] dropout pass is needed:
+ * the LayerNorm epilogue (inner rows), the halo push (the receiver's halo rows, receiver's row index), and the
+ * transposed aggregate / fix-up (the gradient of the dropped tensor).  p == 0 or a NULL pointer: no dropout.
+ */
+typedef struct pg_drop {
+  float p;
+  uint64_t seed;
+  const uint32_t* step_dev;   /* may be NULL: the mask does not depend on a step */
+  int32_t step_off;
+} pg_drop;
+
+/*
  * Neighbour aggregate:
  *   out[r, 0:d] = ( sum_{e in row r} x[indices[e], 0:d] ) / row_div[r]  ( + out[r, 0:d] if r < acc_rows )
  * x and out have element type `dtype`, sums are fp32.  ldx/ldo are row strides in elements.
@@ -88,6 +102,10 @@ typedef struct pg_csr {
  */
 int pg_aggregate(const pg_csr* g, const void* x, int64_t ldx, void* out, int64_t ldo, int32_t d, int dtype,
                  const float* row_div, int32_t acc_rows, float* scratch, void* stream);
+/* the same, with the dropout mask of `drop` applied to every output row as it is written (the backward of
+ * `layer(dropout(F))`: out = mask * ((A^T g) (+ out)) / (1 - p)); element index = row * ceil(d / vec) + vector */
+int pg_aggregate_drop(const pg_csr* g, const void* x, int64_t ldx, void* out, int64_t ldo, int32_t d, int dtype,
+                      const float* row_div, int32_t acc_rows, float* scratch, const pg_drop* drop, void* stream);
 
 /* out[r, 0:d] = x[r, 0:d] / row_div[r]   (gradient of `/ degs`, layer.py:50) */
 int pg_row_div(const void* x, int64_t ldx, void* out, int64_t ldo, int32_t n_rows, int32_t d, int dtype,
@@ -142,10 +160,18 @@ int pg_row_grid(int32_t n_rows);
  * the gradient with the same seed instead of storing a mask (dropout of model.py:47; in place allowed) */
 int pg_dropout(const void* x, int64_t ldx, void* out, int64_t ldo, int32_t n_rows, int32_t d, int dtype, float p,
                uint64_t seed, const uint32_t* step_dev, void* stream);
+/* the same with the general mask key: rows are numbered from row0 (a slice of a larger tensor) */
+int pg_dropout_rows(const void* x, int64_t ldx, void* out, int64_t ldo, int64_t row0, int32_t n_rows, int32_t d, int dtype,
+                    const pg_drop* drop, void* stream);
 /* out = relu?(LayerNorm(y) * gamma + beta), mean/rstd [n_rows] kept for the backward; d % (16/elem) == 0 */
 int pg_ln_relu_fwd(const void* y, int64_t ldy, const float* gamma, const float* beta, float eps, int relu,
                    void* out, int64_t ldo, float* mean, float* rstd, int32_t n_rows, int32_t d, int dtype,
                    void* stream);
+/* the same with the next layer's dropout fused: `out` receives dropout(result) (what the next layer's aggregate and
+ * GEMM read), `out_clean` the result itself (what the halo push sends and the backward needs) */
+int pg_ln_relu_drop_fwd(const void* y, int64_t ldy, const float* gamma, const float* beta, float eps, int relu,
+                        void* out, int64_t ldo, void* out_clean, int64_t ldc, float* mean, float* rstd, int32_t n_rows,
+                        int32_t d, int dtype, const pg_drop* drop, void* stream);
 /* g_y, dgamma[d], dbeta[d] and colsum[d] = column sums of g_y (the bias gradient of the producing linear) */
 int pg_ln_relu_bwd(const void* g_out, int64_t ldg, const void* out, int64_t ldo, const void* y, int64_t ldy,
                    const float* mean, const float* rstd, const float* gamma, int relu, void* g_y, int64_t ldgy,
@@ -179,6 +205,7 @@ typedef struct pg_msg {
   int64_t ld_ema;
   uint32_t* flag;          /* flag word to publish (peer memory), or NULL */
   uint32_t* counter;       /* local arrival counter of this message (self resetting) */
+  int64_t dst_row0;        /* row index of `dst` inside the receiver's tensor (key of the receiver's dropout mask) */
 } pg_msg;
 
 /* rows per CTA used by pg_halo_push when the host fills cta_begin */
@@ -190,6 +217,11 @@ int pg_push_rows_per_cta(void);
  * device, so that a captured CUDA graph of an epoch can be replayed) */
 int pg_halo_push(const pg_msg* msgs, int32_t n_msgs, int32_t n_ctas, const void* src, int64_t ld_src, int32_t d,
                  int dtype, float momentum, float one_minus, uint32_t value, const uint32_t* value_dev, void* stream);
+/* the same with the RECEIVER's dropout applied to every row as it is stored into peer memory (after the EMA, whose
+ * mirror stays clean): the halo rows arrive as the rows of dropout(cat(feat, halo)) the receiver will consume */
+int pg_halo_push_drop(const pg_msg* msgs, int32_t n_msgs, int32_t n_ctas, const void* src, int64_t ld_src, int32_t d,
+                      int dtype, float momentum, float one_minus, uint32_t value, const uint32_t* value_dev,
+                      const pg_drop* drop, void* stream);
 
 /*
  * Block the stream until every flags[i] >= value (acquire, system scope).  A bounded spin:

@@ -35,7 +35,11 @@ class pg_gemm_src(C.Structure):
 class pg_msg(C.Structure):
     _fields_ = [("idx", C.c_void_p), ("src_row0", C.c_int64), ("n_rows", C.c_int32), ("cta_begin", C.c_int32),
                 ("dst", C.c_void_p), ("ld_dst", C.c_int64), ("ema", C.c_void_p), ("ld_ema", C.c_int64),
-                ("flag", C.c_void_p), ("counter", C.c_void_p)]
+                ("flag", C.c_void_p), ("counter", C.c_void_p), ("dst_row0", C.c_int64)]
+
+
+class pg_drop(C.Structure):
+    _fields_ = [("p", C.c_float), ("seed", C.c_uint64), ("step_dev", C.c_void_p), ("step_off", C.c_int32)]
 
 
 def _load():
@@ -50,6 +54,8 @@ def _load():
         "pg_device_info": (C.c_int, [C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(i64)]),
         "pg_set_option": (C.c_int, [C.c_char_p, C.c_int]),
         "pg_aggregate": (C.c_int, [C.POINTER(pg_csr), vp, i64, vp, i64, i32, C.c_int, vp, i32, vp, vp]),
+        "pg_aggregate_drop": (C.c_int, [C.POINTER(pg_csr), vp, i64, vp, i64, i32, C.c_int, vp, i32, vp,
+                                        C.POINTER(pg_drop), vp]),
         "pg_row_div": (C.c_int, [vp, i64, vp, i64, i32, i32, C.c_int, vp, vp]),
         "pg_linear": (C.c_int, [C.c_int, C.c_int, C.POINTER(pg_gemm_src), i32, vp, vp, vp, i64, i32, i32, vp]),
         "pg_wgrad_workspace": (i64, [i32, i32, i32, C.c_int]),
@@ -57,6 +63,9 @@ def _load():
         "pg_split_tf32": (C.c_int, [vp, i64, vp, vp, i64, i32, i32, vp]),
         "pg_row_grid": (C.c_int, [i32]),
         "pg_dropout": (C.c_int, [vp, i64, vp, i64, i32, i32, C.c_int, f32, C.c_uint64, vp, vp]),
+        "pg_dropout_rows": (C.c_int, [vp, i64, vp, i64, i64, i32, i32, C.c_int, C.POINTER(pg_drop), vp]),
+        "pg_ln_relu_drop_fwd": (C.c_int, [vp, i64, vp, vp, f32, C.c_int, vp, i64, vp, i64, vp, vp, i32, i32, C.c_int,
+                                          C.POINTER(pg_drop), vp]),
         "pg_ln_relu_fwd": (C.c_int, [vp, i64, vp, vp, f32, C.c_int, vp, i64, vp, vp, i32, i32, C.c_int, vp]),
         "pg_ln_relu_bwd": (C.c_int, [vp, i64, vp, i64, vp, i64, vp, vp, vp, C.c_int, vp, i64, vp, vp, vp, vp, i32, i32,
                                      C.c_int, vp]),
@@ -64,6 +73,7 @@ def _load():
         "pg_ce_bwd": (C.c_int, [vp, i64, vp, vp, vp, i32, i32, i32, C.c_int, vp, i64, vp, vp, vp]),
         "pg_push_rows_per_cta": (C.c_int, []),
         "pg_halo_push": (C.c_int, [vp, i32, i32, vp, i64, i32, C.c_int, f32, f32, u32, vp, vp]),
+        "pg_halo_push_drop": (C.c_int, [vp, i32, i32, vp, i64, i32, C.c_int, f32, f32, u32, vp, C.POINTER(pg_drop), vp]),
         "pg_halo_wait": (C.c_int, [vp, i32, u32, vp, i32, vp, vp, vp]),
         "pg_scale_rows": (C.c_int, [vp, i64, vp, i64, i32, i32, C.c_int, f32, C.c_int, i32, vp, vp]),
         "pg_boundary_add": (C.c_int, [vp, i64, vp, i64, i32, C.c_int, vp, vp, vp, i32, vp]),

@@ -18,7 +18,7 @@ namespace pg {
 template <typename T, int VB, int G, int VPL, int U>
 __global__ void __launch_bounds__(256)
 agg_kernel(pg_csr g, const T* __restrict__ x, uint32_t ldx_bytes, T* __restrict__ out, int64_t ldo, int nvec,
-           const float* __restrict__ row_div, int acc_rows, float* __restrict__ scratch, int64_t lds) {
+           const float* __restrict__ row_div, int acc_rows, float* __restrict__ scratch, int64_t lds, DropArg drop) {
   using P = Pack<T, VB>;
   using Raw = typename P::Raw;
   constexpr int V = P::V;
@@ -118,6 +118,8 @@ agg_kernel(pg_csr g, const T* __restrict__ x, uint32_t ldx_bytes, T* __restrict_
 #pragma unroll
           for (int i = 0; i < V; ++i) r[i] += ov[i];
         }
+        if (drop.thresh16 != 0u)
+          drop_apply<V>(r, static_cast<uint64_t>(row) * nvec + (c0 + lane_g + j * G), drop.thresh16, drop.scale, drop.seed_lo, drop_seed_hi(drop));
         st_vec<VB>(op + o, P::pack(r));
       }
     }
@@ -130,7 +132,7 @@ agg_kernel(pg_csr g, const T* __restrict__ x, uint32_t ldx_bytes, T* __restrict_
 template <typename T, int VB>
 __global__ void __launch_bounds__(256)
 agg_fixup_kernel(pg_csr g, T* __restrict__ out, int64_t ldo, int nvec, const float* __restrict__ row_div,
-                 int acc_rows, const float* __restrict__ scratch, int64_t lds) {
+                 int acc_rows, const float* __restrict__ scratch, int64_t lds, DropArg drop) {
   using P = Pack<T, VB>;
   constexpr int V = P::V;
   __shared__ float part[8][32 * V];
@@ -180,6 +182,8 @@ agg_fixup_kernel(pg_csr g, T* __restrict__ out, int64_t ldo, int nvec, const flo
 #pragma unroll
         for (int i = 0; i < V; ++i) r[i] += o[i];
       }
+      if (drop.thresh16 != 0u)
+        drop_apply<V>(r, static_cast<uint64_t>(row) * nvec + vi, drop.thresh16, drop.scale, drop.seed_lo, drop_seed_hi(drop));
       st_vec<VB>(op + static_cast<int64_t>(vi) * V, P::pack(r));
     }
     __syncthreads();
@@ -261,6 +265,9 @@ struct Agg2 {
   int64_t ldo;
   int col0;                 // first vector column of this lane (c0 + lane)
   int acc_rows;
+  int nvec;
+  DropArg drop;             // dropout applied to every row as it is written (thresh16 == 0: none)
+  uint32_t drop_hi;
   float2 acc[VPL][NA];
 
   __device__ __forceinline__ void zero() {
@@ -314,6 +321,8 @@ struct Agg2 {
 #pragma unroll
           for (int i = 0; i < V; ++i) r[i] += ov[i];
         }
+        if (drop.thresh16 != 0u)
+          drop_apply<V>(r, static_cast<uint64_t>(row) * nvec + (col0 + j * 32), drop.thresh16, drop.scale, drop.seed_lo, drop_hi);
         if (HINT) st_vec_cs<VB>(op + o, P::pack(r));
         else st_vec<VB>(op + o, P::pack(r));
       }
@@ -377,11 +386,15 @@ struct Agg2 {
 };
 
 template <typename A, typename T>
-__device__ __forceinline__ void agg2_setup(A& a, const T* x, uint32_t ldx_bytes, T* out, int64_t ldo, int acc_rows) {
+__device__ __forceinline__ void agg2_setup(A& a, const T* x, uint32_t ldx_bytes, T* out, int64_t ldo, int acc_rows, int nvec,
+                                           const DropArg& drop) {
   a.ldx_bytes = ldx_bytes;
   a.out = out;
   a.ldo = ldo;
   a.acc_rows = acc_rows;
+  a.nvec = nvec;
+  a.drop = drop;
+  a.drop_hi = drop_seed_hi(drop);
   a.pol_hot = a.pol_cold = 0;
 }
 template <typename A, typename T>
@@ -400,7 +413,7 @@ __device__ __forceinline__ void agg2_columns(A& a, const T* x, int c0, int lane,
 template <typename T, int VB, int VPL, int U, bool HINT, int OCC>
 __global__ void __launch_bounds__(256, (VPL == 1 ? OCC : (VPL == 2 ? 2 : 1)))
 agg2_long_kernel(pg_csr g, const T* __restrict__ x, uint32_t ldx_bytes, T* __restrict__ out, int64_t ldo, int nvec,
-                 const float* __restrict__ row_div, int acc_rows, float* __restrict__ scratch, int64_t lds) {
+                 const float* __restrict__ row_div, int acc_rows, float* __restrict__ scratch, int64_t lds, DropArg drop) {
   using A = Agg2<T, VB, VPL, U, HINT>;
   constexpr int V = A::V;
   const int lane = threadIdx.x & 31;
@@ -409,7 +422,7 @@ agg2_long_kernel(pg_csr g, const T* __restrict__ x, uint32_t ldx_bytes, T* __res
   const int4 c = __ldcs(reinterpret_cast<const int4*>(g.chunks) + cid);
   const uint32_t* __restrict__ pidx = reinterpret_cast<const uint32_t*>(g.pidx) + c.x;
   A a;
-  agg2_setup(a, x, ldx_bytes, out, ldo, acc_rows);
+  agg2_setup(a, x, ldx_bytes, out, ldo, acc_rows, nvec, drop);
   if (HINT) {
     a.pol_hot = l2_policy_evict_last();
     a.pol_cold = l2_policy_evict_first();
@@ -456,7 +469,7 @@ template <int N> __device__ __forceinline__ void cp_async_wait() {
 template <typename T, int VPL, int D, bool HINT>
 __global__ void __launch_bounds__(256, (VPL == 1 ? 6 : 3))
 agg3_long_kernel(pg_csr g, const T* __restrict__ x, uint32_t ldx_bytes, T* __restrict__ out, int64_t ldo, int nvec,
-                 const float* __restrict__ row_div, int acc_rows, float* __restrict__ scratch, int64_t lds) {
+                 const float* __restrict__ row_div, int acc_rows, float* __restrict__ scratch, int64_t lds, DropArg drop) {
   using A = Agg2<T, 16, VPL, 1, HINT>;
   using Raw = typename A::Raw;
   constexpr int V = A::V;
@@ -472,7 +485,7 @@ agg3_long_kernel(pg_csr g, const T* __restrict__ x, uint32_t ldx_bytes, T* __res
   // this lane's 16 bytes of slot 0 (piece j at + j * 512)
   const uint32_t ring = static_cast<uint32_t>(__cvta_generic_to_shared(agg3_ring)) + warp * (D * kSlotBytes) + lane * 16;
   A a;
-  agg2_setup(a, x, ldx_bytes, out, ldo, acc_rows);
+  agg2_setup(a, x, ldx_bytes, out, ldo, acc_rows, nvec, drop);
   if (HINT) {
     a.pol_hot = l2_policy_evict_last();
     a.pol_cold = l2_policy_evict_first();
@@ -537,7 +550,7 @@ agg3_long_kernel(pg_csr g, const T* __restrict__ x, uint32_t ldx_bytes, T* __res
 template <typename T, int VB, int VPL, int U, bool HINT>
 __global__ void __launch_bounds__(256, (VPL == 1 ? 4 : (VPL == 2 ? 2 : 1)))
 agg2_small_kernel(pg_csr g, const T* __restrict__ x, uint32_t ldx_bytes, T* __restrict__ out, int64_t ldo, int nvec,
-                  const float* __restrict__ row_div, int acc_rows) {
+                  const float* __restrict__ row_div, int acc_rows, DropArg drop) {
   using A = Agg2<T, VB, VPL, U, HINT>;
   const int lane = threadIdx.x & 31;
   const int cid = g.n_chunks_long + blockIdx.x * 8 + (threadIdx.x >> 5);
@@ -552,7 +565,7 @@ agg2_small_kernel(pg_csr g, const T* __restrict__ x, uint32_t ldx_bytes, T* __re
     if (row_div != nullptr) my_inv = 1.f / __ldg(row_div + my_row);
   }
   A a;
-  agg2_setup(a, x, ldx_bytes, out, ldo, acc_rows);
+  agg2_setup(a, x, ldx_bytes, out, ldo, acc_rows, nvec, drop);
   if (HINT) {
     a.pol_hot = l2_policy_evict_last();
     a.pol_cold = l2_policy_evict_first();
@@ -587,7 +600,7 @@ static AggSide* agg_side_for(cudaStream_t st) {
 
 template <typename T, int VB, int VPL, bool HINT>
 static int launch_agg2h(const pg_csr& g, const T* x, int64_t ldx, T* out, int64_t ldo, int nvec,
-                        const float* row_div, int acc_rows, float* scratch, int64_t lds, cudaStream_t st) {
+                        const float* row_div, int acc_rows, float* scratch, int64_t lds, const DropArg& da, cudaStream_t st) {
   constexpr int U = (VPL >= 4) ? 2 : (VPL == 2 ? 4 : 8);
   const uint32_t ldxb = static_cast<uint32_t>(ldx * sizeof(T));
   AggSide* side = nullptr;
@@ -599,7 +612,7 @@ static int launch_agg2h(const pg_csr& g, const T* x, int64_t ldx, T* out, int64_
       PG_CHECK_CUDA(cudaStreamWaitEvent(side->side, side->fork, 0));
       ss = side->side;
     }
-    agg2_small_kernel<T, VB, VPL, U, HINT><<<blocks, 256, 0, ss>>>(g, x, ldxb, out, ldo, nvec, row_div, acc_rows);
+    agg2_small_kernel<T, VB, VPL, U, HINT><<<blocks, 256, 0, ss>>>(g, x, ldxb, out, ldo, nvec, row_div, acc_rows, da);
     PG_LAUNCH_CHECK();
     if (side != nullptr) PG_CHECK_CUDA(cudaEventRecord(side->join, ss));
   }
@@ -613,18 +626,18 @@ static int launch_agg2h(const pg_csr& g, const T* x, int64_t ldx, T* out, int64_
       PG_CHECK_CUDA(cudaFuncSetAttribute(agg3_long_kernel<T, VPL, D, HINT>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
       attr_done = true;
     }
-    agg3_long_kernel<T, VPL, D, HINT><<<blocks, 256, smem, st>>>(g, x, ldxb, out, ldo, nvec, row_div, acc_rows, scratch, lds);
+    agg3_long_kernel<T, VPL, D, HINT><<<blocks, 256, smem, st>>>(g, x, ldxb, out, ldo, nvec, row_div, acc_rows, scratch, lds, da);
     PG_LAUNCH_CHECK();
   } else if (g.n_chunks_long > 0) {
     const unsigned blocks = static_cast<unsigned>((g.n_chunks_long + 7) / 8);
     if (VPL == 1 && g_agg_occ == 5)
-      agg2_long_kernel<T, VB, VPL, U, HINT, (VPL == 1 ? 5 : 4)><<<blocks, 256, 0, st>>>(g, x, ldxb, out, ldo, nvec, row_div, acc_rows, scratch, lds);
+      agg2_long_kernel<T, VB, VPL, U, HINT, (VPL == 1 ? 5 : 4)><<<blocks, 256, 0, st>>>(g, x, ldxb, out, ldo, nvec, row_div, acc_rows, scratch, lds, da);
     else
-      agg2_long_kernel<T, VB, VPL, U, HINT, 4><<<blocks, 256, 0, st>>>(g, x, ldxb, out, ldo, nvec, row_div, acc_rows, scratch, lds);
+      agg2_long_kernel<T, VB, VPL, U, HINT, 4><<<blocks, 256, 0, st>>>(g, x, ldxb, out, ldo, nvec, row_div, acc_rows, scratch, lds, da);
     PG_LAUNCH_CHECK();
   }
   if (g.n_long > 0) {
-    agg_fixup_kernel<T, VB><<<g.n_long, 256, 0, st>>>(g, out, ldo, nvec, row_div, acc_rows, scratch, lds);
+    agg_fixup_kernel<T, VB><<<g.n_long, 256, 0, st>>>(g, out, ldo, nvec, row_div, acc_rows, scratch, lds, da);
     PG_LAUNCH_CHECK();
   }
   if (side != nullptr) PG_CHECK_CUDA(cudaStreamWaitEvent(st, side->join, 0));
@@ -633,9 +646,9 @@ static int launch_agg2h(const pg_csr& g, const T* x, int64_t ldx, T* out, int64_
 
 template <typename T, int VB, int VPL>
 static int launch_agg2(const pg_csr& g, const T* x, int64_t ldx, T* out, int64_t ldo, int nvec,
-                       const float* row_div, int acc_rows, float* scratch, int64_t lds, cudaStream_t st) {
-  if (g_agg_l2_hint) return launch_agg2h<T, VB, VPL, true>(g, x, ldx, out, ldo, nvec, row_div, acc_rows, scratch, lds, st);
-  return launch_agg2h<T, VB, VPL, false>(g, x, ldx, out, ldo, nvec, row_div, acc_rows, scratch, lds, st);
+                       const float* row_div, int acc_rows, float* scratch, int64_t lds, const DropArg& da, cudaStream_t st) {
+  if (g_agg_l2_hint) return launch_agg2h<T, VB, VPL, true>(g, x, ldx, out, ldo, nvec, row_div, acc_rows, scratch, lds, da, st);
+  return launch_agg2h<T, VB, VPL, false>(g, x, ldx, out, ldo, nvec, row_div, acc_rows, scratch, lds, da, st);
 }
 
 int g_agg_pack_short = 0;   // pg_set_option("agg_pack_short", 0|1): 16 lanes x 2 vectors per row when rows are short.
@@ -643,30 +656,30 @@ int g_agg_pack_short = 0;   // pg_set_option("agg_pack_short", 0|1): 16 lanes x 
 
 template <typename T, int VB, int G, int VPL, int U>
 static int launch_agg_u(const pg_csr& g, const T* x, int64_t ldx, T* out, int64_t ldo, int nvec,
-                        const float* row_div, int acc_rows, float* scratch, int64_t lds, cudaStream_t st);
+                        const float* row_div, int acc_rows, float* scratch, int64_t lds, const DropArg& da, cudaStream_t st);
 
 template <typename T, int VB, int G, int VPL>
 static int launch_agg(const pg_csr& g, const T* x, int64_t ldx, T* out, int64_t ldo, int nvec,
-                      const float* row_div, int acc_rows, float* scratch, int64_t lds, cudaStream_t st) {
+                      const float* row_div, int acc_rows, float* scratch, int64_t lds, const DropArg& da, cudaStream_t st) {
   if (VPL == 1 && g_agg_unroll == 4)
-    return launch_agg_u<T, VB, G, VPL, 4>(g, x, ldx, out, ldo, nvec, row_div, acc_rows, scratch, lds, st);
+    return launch_agg_u<T, VB, G, VPL, 4>(g, x, ldx, out, ldo, nvec, row_div, acc_rows, scratch, lds, da, st);
   constexpr int U = (VPL >= 4) ? 2 : (VPL == 2 ? 4 : 8);
-  return launch_agg_u<T, VB, G, VPL, U>(g, x, ldx, out, ldo, nvec, row_div, acc_rows, scratch, lds, st);
+  return launch_agg_u<T, VB, G, VPL, U>(g, x, ldx, out, ldo, nvec, row_div, acc_rows, scratch, lds, da, st);
 }
 
 template <typename T, int VB, int G, int VPL, int U>
 static int launch_agg_u(const pg_csr& g, const T* x, int64_t ldx, T* out, int64_t ldo, int nvec,
-                        const float* row_div, int acc_rows, float* scratch, int64_t lds, cudaStream_t st) {
+                        const float* row_div, int acc_rows, float* scratch, int64_t lds, const DropArg& da, cudaStream_t st) {
   constexpr int GROUPS = 256 / G;
   const int64_t n_items = static_cast<int64_t>(g.n_rows) + g.n_seg;
   if (n_items > 0) {
     const int64_t blocks = (n_items + GROUPS - 1) / GROUPS;
     agg_kernel<T, VB, G, VPL, U><<<static_cast<unsigned>(blocks), 256, 0, st>>>(g, x, static_cast<uint32_t>(ldx * sizeof(T)), out, ldo, nvec, row_div,
-                                                                                acc_rows, scratch, lds);
+                                                                                acc_rows, scratch, lds, da);
     PG_LAUNCH_CHECK();
   }
   if (g.n_long > 0) {
-    agg_fixup_kernel<T, VB><<<g.n_long, 256, 0, st>>>(g, out, ldo, nvec, row_div, acc_rows, scratch, lds);
+    agg_fixup_kernel<T, VB><<<g.n_long, 256, 0, st>>>(g, out, ldo, nvec, row_div, acc_rows, scratch, lds, da);
     PG_LAUNCH_CHECK();
   }
   return PG_OK;
@@ -674,12 +687,12 @@ static int launch_agg_u(const pg_csr& g, const T* x, int64_t ldx, T* out, int64_
 
 template <typename T, int VB>
 static int dispatch_agg(const pg_csr& g, const T* x, int64_t ldx, T* out, int64_t ldo, int nvec,
-                        const float* row_div, int acc_rows, float* scratch, int64_t lds, cudaStream_t st) {
-#define PG_AGG(G_, VPL_) return launch_agg<T, VB, G_, VPL_>(g, x, ldx, out, ldo, nvec, row_div, acc_rows, scratch, lds, st)
+                        const float* row_div, int acc_rows, float* scratch, int64_t lds, const DropArg& da, cudaStream_t st) {
+#define PG_AGG(G_, VPL_) return launch_agg<T, VB, G_, VPL_>(g, x, ldx, out, ldo, nvec, row_div, acc_rows, scratch, lds, da, st)
   if (g_agg_impl >= 2 && g.chunks != nullptr && nvec > 16) {
-    if (nvec <= 32) return launch_agg2<T, VB, 1>(g, x, ldx, out, ldo, nvec, row_div, acc_rows, scratch, lds, st);
-    if (nvec <= 64) return launch_agg2<T, VB, 2>(g, x, ldx, out, ldo, nvec, row_div, acc_rows, scratch, lds, st);
-    return launch_agg2<T, VB, 4>(g, x, ldx, out, ldo, nvec, row_div, acc_rows, scratch, lds, st);
+    if (nvec <= 32) return launch_agg2<T, VB, 1>(g, x, ldx, out, ldo, nvec, row_div, acc_rows, scratch, lds, da, st);
+    if (nvec <= 64) return launch_agg2<T, VB, 2>(g, x, ldx, out, ldo, nvec, row_div, acc_rows, scratch, lds, da, st);
+    return launch_agg2<T, VB, 4>(g, x, ldx, out, ldo, nvec, row_div, acc_rows, scratch, lds, da, st);
   }
   if (nvec <= 4) PG_AGG(4, 1);
   if (nvec <= 8) PG_AGG(8, 1);
@@ -695,7 +708,7 @@ static int dispatch_agg(const pg_csr& g, const T* x, int64_t ldx, T* out, int64_
 
 template <typename T>
 static int aggregate_t(const pg_csr& g, const void* x, int64_t ldx, void* out, int64_t ldo, int d,
-                       const float* row_div, int acc_rows, float* scratch, cudaStream_t st) {
+                       const float* row_div, int acc_rows, float* scratch, const DropArg& da, cudaStream_t st) {
   const int es = sizeof(T);
   int vb = min(vec_bytes(x, ldx, es), vec_bytes(out, ldo, es));
   // a vector must not straddle two rows: either d is a multiple of the vector or both strides leave room
@@ -709,12 +722,13 @@ static int aggregate_t(const pg_csr& g, const void* x, int64_t ldx, void* out, i
   const int nvec = static_cast<int>(round_up(d, v) / v);
   const int64_t lds = round_up(d, 8);
   PG_REQUIRE(g.n_seg == 0 || scratch != nullptr, "pg_aggregate: scratch is NULL but the graph has %d long-row segments", g.n_seg);
+  PG_REQUIRE(da.thresh16 == 0u || vb == 16, "pg_aggregate_drop: the dropout mask is defined on 16-byte vectors (rows must be 16-byte aligned and padded)");
   const T* xp = static_cast<const T*>(x);
   T* op = static_cast<T*>(out);
   switch (vb) {
-    case 16: return dispatch_agg<T, 16>(g, xp, ldx, op, ldo, nvec, row_div, acc_rows, scratch, lds, st);
-    case 8: return dispatch_agg<T, 8>(g, xp, ldx, op, ldo, nvec, row_div, acc_rows, scratch, lds, st);
-    case 4: return dispatch_agg<T, 4>(g, xp, ldx, op, ldo, nvec, row_div, acc_rows, scratch, lds, st);
+    case 16: return dispatch_agg<T, 16>(g, xp, ldx, op, ldo, nvec, row_div, acc_rows, scratch, lds, da, st);
+    case 8: return dispatch_agg<T, 8>(g, xp, ldx, op, ldo, nvec, row_div, acc_rows, scratch, lds, da, st);
+    case 4: return dispatch_agg<T, 4>(g, xp, ldx, op, ldo, nvec, row_div, acc_rows, scratch, lds, da, st);
     default:
       set_error("pg_aggregate: rows must be at least 4-byte aligned (vector width %d)", vb);
       return PG_ERR_INVALID;
@@ -807,12 +821,18 @@ extern "C" int pg_set_option(const char* name, int value) {
 
 extern "C" int pg_aggregate(const pg_csr* g, const void* x, int64_t ldx, void* out, int64_t ldo, int32_t d, int dtype,
                             const float* row_div, int32_t acc_rows, float* scratch, void* stream) {
+  return pg_aggregate_drop(g, x, ldx, out, ldo, d, dtype, row_div, acc_rows, scratch, nullptr, stream);
+}
+
+extern "C" int pg_aggregate_drop(const pg_csr* g, const void* x, int64_t ldx, void* out, int64_t ldo, int32_t d, int dtype,
+                                 const float* row_div, int32_t acc_rows, float* scratch, const pg_drop* drop, void* stream) {
+  const pg::DropArg da = pg::make_drop(drop);
   PG_REQUIRE(g && x && out, "pg_aggregate: null argument");
   PG_REQUIRE(g->n_rows >= 0 && g->seg_len > 0 && d > 0, "pg_aggregate: bad sizes (n_rows=%d seg_len=%d d=%d)", g->n_rows, g->seg_len, d);
   PG_REQUIRE(ldx >= d && ldo >= d && ldx < (1ll << 29), "pg_aggregate: row stride smaller than d (or >= 2^29 elements)");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (dtype == PG_F32) return pg::aggregate_t<float>(*g, x, ldx, out, ldo, d, row_div, acc_rows, scratch, st);
-  if (dtype == PG_BF16) return pg::aggregate_t<__nv_bfloat16>(*g, x, ldx, out, ldo, d, row_div, acc_rows, scratch, st);
+  if (dtype == PG_F32) return pg::aggregate_t<float>(*g, x, ldx, out, ldo, d, row_div, acc_rows, scratch, da, st);
+  if (dtype == PG_BF16) return pg::aggregate_t<__nv_bfloat16>(*g, x, ldx, out, ldo, d, row_div, acc_rows, scratch, da, st);
   pg::set_error("pg_aggregate: unknown dtype %d", dtype);
   return PG_ERR_INVALID;
 }

@@ -121,6 +121,49 @@ template <int VB> struct Pack<__nv_bfloat16, VB> {
   }
 };
 
+// ---- dropout with a counter-based generator -------------------------------------------------------------------------
+// keep(i, k) is a pure function of (seed, step, element): i = row * nvec + (16-byte vector index inside the row), k =
+// element inside the vector; 16 random bits per element, two elements per hash.  Every kernel that produces or consumes
+// a dropped tensor (pg_dropout, the LayerNorm epilogue, the halo push, the aggregate / fix-up store) evaluates the SAME
+// function, so a mask is never stored: out = keep ? x / (1 - p) : 0.
+struct DropArg {
+  uint32_t thresh16;           // p * 65536 (0: no dropout)
+  float scale;                 // 1 / (1 - p)
+  uint32_t seed_lo, seed_hi;
+  const uint32_t* step_dev;    // device-side epoch counter (may be null: no step mixing)
+  int32_t step_off;
+};
+__device__ __forceinline__ uint32_t mix32(uint32_t x) {       // lowbias32 finaliser
+  x ^= x >> 16; x *= 0x7feb352dU; x ^= x >> 15; x *= 0x846ca68bU; x ^= x >> 16;
+  return x;
+}
+__device__ __forceinline__ uint32_t drop_seed_hi(const DropArg& a) {
+  return a.step_dev != nullptr ? a.seed_hi + 0x632be5abU * (*a.step_dev + static_cast<uint32_t>(a.step_off) + 1u) : a.seed_hi;
+}
+template <int V>
+__device__ __forceinline__ void drop_apply(float (&f)[V], uint64_t i, uint32_t thresh16, float scale, uint32_t seed_lo,
+                                           uint32_t seed_hi) {
+  const uint32_t base = mix32(static_cast<uint32_t>(i) ^ seed_lo) ^ mix32(static_cast<uint32_t>(i >> 32) + seed_hi);
+#pragma unroll
+  for (int k = 0; k < V; k += 2) {
+    const uint32_t h = mix32(base + 0x9e3779b9U * (k / 2 + 1));
+    f[k] = ((h & 0xffffU) >= thresh16) ? f[k] * scale : 0.f;
+    if (k + 1 < V) f[k + 1] = ((h >> 16) >= thresh16) ? f[k + 1] * scale : 0.f;
+  }
+}
+inline DropArg make_drop(const pg_drop* d) {
+  DropArg a{0u, 1.f, 0u, 0u, nullptr, 0};
+  if (d != nullptr && d->p > 0.f) {
+    a.thresh16 = static_cast<uint32_t>(d->p * 65536.0f + 0.5f);
+    a.scale = 1.0f / (1.0f - d->p);
+    a.seed_lo = static_cast<uint32_t>(d->seed);
+    a.seed_hi = static_cast<uint32_t>(d->seed >> 32);
+    a.step_dev = d->step_dev;
+    a.step_off = d->step_off;
+  }
+  return a;
+}
+
 __host__ __device__ inline int64_t round_up(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
 
 // largest power-of-two vector width (bytes, <= 16) that divides both the byte stride of a row

@@ -24,8 +24,9 @@ __device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
 template <typename T, int VB>
 __global__ void __launch_bounds__(kPushThreads)
 halo_push_kernel(const pg_msg* __restrict__ msgs, int n_msgs, const T* __restrict__ src, int64_t ld_src, int nvec,
-                 float momentum, float one_minus, uint32_t value, const uint32_t* __restrict__ value_dev) {
+                 float momentum, float one_minus, uint32_t value, const uint32_t* __restrict__ value_dev, DropArg drop) {
   if (value_dev != nullptr) value += *value_dev;     // epoch counter kept on the device (CUDA-graph replay)
+  const uint32_t drop_hi = drop_seed_hi(drop);
   using P = Pack<T, VB>;
   using Raw = typename P::Raw;
   constexpr int V = P::V;
@@ -44,7 +45,13 @@ halo_push_kernel(const pg_msg* __restrict__ msgs, int n_msgs, const T* __restric
     T* dp = dst + static_cast<int64_t>(r) * msg.ld_dst;
     if (msg.ema == nullptr) {
       for (int vi = lane; vi < nvec; vi += 32) {
-        const Raw v = *reinterpret_cast<const Raw*>(sp + static_cast<int64_t>(vi) * V);
+        Raw v = *reinterpret_cast<const Raw*>(sp + static_cast<int64_t>(vi) * V);
+        if (drop.thresh16 != 0u) {               // the receiver's dropout of its row dst_row0 + r
+          float f[V];
+          P::unpack(v, f);
+          drop_apply<V>(f, static_cast<uint64_t>(msg.dst_row0 + r) * nvec + vi, drop.thresh16, drop.scale, drop.seed_lo, drop_hi);
+          v = P::pack(f);
+        }
         st_vec<VB>(dp + static_cast<int64_t>(vi) * V, v);
       }
     } else {
@@ -59,6 +66,11 @@ halo_push_kernel(const pg_msg* __restrict__ msgs, int n_msgs, const T* __restric
           const float t = __fmul_rn(e[i], momentum);
           f[i] = __fadd_rn(t, __fmul_rn(one_minus, f[i]));
           e[i] = f[i];
+        }
+        if (drop.thresh16 != 0u) {               // the mirror stays clean; what travels is dropout(round(ema))
+          const Raw c = P::pack(f);
+          P::unpack(c, f);
+          drop_apply<V>(f, static_cast<uint64_t>(msg.dst_row0 + r) * nvec + vi, drop.thresh16, drop.scale, drop.seed_lo, drop_hi);
         }
         st_vec<VB>(dp + static_cast<int64_t>(vi) * V, P::pack(f));
       }
@@ -192,16 +204,17 @@ static int common_vec(int d, int es, int vb, std::initializer_list<int64_t> lds)
 
 template <typename T>
 static int halo_push_t(const pg_msg* msgs, int n_msgs, int n_ctas, const void* src, int64_t ld_src, int d,
-                       int vb, float momentum, float one_minus, uint32_t value, const uint32_t* value_dev, cudaStream_t st) {
+                       int vb, float momentum, float one_minus, uint32_t value, const uint32_t* value_dev, const DropArg& da,
+                       cudaStream_t st) {
   const int es = sizeof(T);
   const int v = vb / es;
   const int nvec = static_cast<int>(round_up(d, v) / v);
   const T* sp = static_cast<const T*>(src);
   if (n_ctas > 0) {
     switch (vb) {
-      case 16: halo_push_kernel<T, 16><<<n_ctas, kPushThreads, 0, st>>>(msgs, n_msgs, sp, ld_src, nvec, momentum, one_minus, value, value_dev); break;
-      case 8: halo_push_kernel<T, 8><<<n_ctas, kPushThreads, 0, st>>>(msgs, n_msgs, sp, ld_src, nvec, momentum, one_minus, value, value_dev); break;
-      case 4: halo_push_kernel<T, 4><<<n_ctas, kPushThreads, 0, st>>>(msgs, n_msgs, sp, ld_src, nvec, momentum, one_minus, value, value_dev); break;
+      case 16: halo_push_kernel<T, 16><<<n_ctas, kPushThreads, 0, st>>>(msgs, n_msgs, sp, ld_src, nvec, momentum, one_minus, value, value_dev, da); break;
+      case 8: halo_push_kernel<T, 8><<<n_ctas, kPushThreads, 0, st>>>(msgs, n_msgs, sp, ld_src, nvec, momentum, one_minus, value, value_dev, da); break;
+      case 4: halo_push_kernel<T, 4><<<n_ctas, kPushThreads, 0, st>>>(msgs, n_msgs, sp, ld_src, nvec, momentum, one_minus, value, value_dev, da); break;
       default: set_error("pg_halo_push: unsupported vector width %d", vb); return PG_ERR_INVALID;
     }
     PG_LAUNCH_CHECK();
@@ -219,6 +232,12 @@ extern "C" int pg_push_rows_per_cta(void) { return pg::kPushRows; }
 extern "C" int pg_halo_push(const pg_msg* msgs, int32_t n_msgs, int32_t n_ctas, const void* src, int64_t ld_src,
                             int32_t d, int dtype, float momentum, float one_minus, uint32_t value, const uint32_t* value_dev,
                             void* stream) {
+  return pg_halo_push_drop(msgs, n_msgs, n_ctas, src, ld_src, d, dtype, momentum, one_minus, value, value_dev, nullptr, stream);
+}
+
+extern "C" int pg_halo_push_drop(const pg_msg* msgs, int32_t n_msgs, int32_t n_ctas, const void* src, int64_t ld_src,
+                                 int32_t d, int dtype, float momentum, float one_minus, uint32_t value,
+                                 const uint32_t* value_dev, const pg_drop* drop, void* stream) {
   PG_REQUIRE(msgs && n_msgs > 0, "pg_halo_push: no messages");
   PG_REQUIRE(src != nullptr || n_ctas == 0, "pg_halo_push: null source");
   PG_REQUIRE(d > 0 && ld_src >= d, "pg_halo_push: bad sizes");
@@ -227,9 +246,11 @@ extern "C" int pg_halo_push(const pg_msg* msgs, int32_t n_msgs, int32_t n_ctas, 
   // destination strides equal the padded source stride by construction; use what src allows
   int vb = pg::vec_bytes(src, ld_src, es);
   vb = pg::common_vec(d, es, vb, {ld_src});
+  const pg::DropArg da = pg::make_drop(drop);
+  PG_REQUIRE(da.thresh16 == 0u || vb == 16, "pg_halo_push_drop: the dropout mask is defined on 16-byte vectors (rows must be 16-byte aligned)");
   int rc;
-  if (dtype == PG_F32) rc = pg::halo_push_t<float>(msgs, n_msgs, n_ctas, src, ld_src, d, vb, momentum, one_minus, value, value_dev, st);
-  else if (dtype == PG_BF16) rc = pg::halo_push_t<__nv_bfloat16>(msgs, n_msgs, n_ctas, src, ld_src, d, vb, momentum, one_minus, value, value_dev, st);
+  if (dtype == PG_F32) rc = pg::halo_push_t<float>(msgs, n_msgs, n_ctas, src, ld_src, d, vb, momentum, one_minus, value, value_dev, da, st);
+  else if (dtype == PG_BF16) rc = pg::halo_push_t<__nv_bfloat16>(msgs, n_msgs, n_ctas, src, ld_src, d, vb, momentum, one_minus, value, value_dev, da, st);
   else { pg::set_error("pg_halo_push: unknown dtype %d", dtype); return PG_ERR_INVALID; }
   if (rc != PG_OK) return rc;
   pg::halo_flag_only_kernel<<<(n_msgs + 63) / 64, 64, 0, st>>>(msgs, n_msgs, value, value_dev);

@@ -25,13 +25,14 @@ template <typename T, int VPL, int R>
 __global__ void __launch_bounds__(kRowThreads)
 ln_relu_fwd_kernel(const T* __restrict__ y, int64_t ldy, const float* __restrict__ gamma, const float* __restrict__ beta,
                    float eps, int relu, T* __restrict__ out, int64_t ldo, float* __restrict__ mean_out,
-                   float* __restrict__ rstd_out, int n_rows, int d) {
+                   float* __restrict__ rstd_out, int n_rows, int d, T* __restrict__ out_clean, int64_t ldc, DropArg drop) {
   using P = Pack<T, 16>;
   using Raw = typename P::Raw;
   constexpr int V = P::V;
   const int lane = threadIdx.x & 31;
   const int warps = (gridDim.x * kRowThreads) >> 5;
   const int nvec = d / V;
+  const uint32_t seed_hi = drop_seed_hi(drop);
   float gm[VPL][V], bt[VPL][V];
 #pragma unroll
   for (int j = 0; j < VPL; ++j)
@@ -80,7 +81,18 @@ ln_relu_fwd_kernel(const T* __restrict__ y, int64_t ldy, const float* __restrict
             const float v = (x[j][i] - mean) * rstd * gm[j][i] + bt[j][i];
             o[i] = (relu && v < 0.f) ? 0.f : v;
           }
-          st_vec<16>(out + static_cast<int64_t>(row) * ldo + static_cast<int64_t>(lane + j * 32) * V, P::pack(o));
+          Raw packed = P::pack(o);
+          if (out_clean != nullptr) {
+            // the clean result (halo push source, backward), and dropout(result) for the next layer -- computed from
+            // the ROUNDED clean value, i.e. exactly what pg_dropout would make of `out_clean`
+            st_vec<16>(out_clean + static_cast<int64_t>(row) * ldc + static_cast<int64_t>(lane + j * 32) * V, packed);
+            if (drop.thresh16 != 0u) {
+              P::unpack(packed, o);
+              drop_apply<V>(o, static_cast<uint64_t>(row) * nvec + (lane + j * 32), drop.thresh16, drop.scale, drop.seed_lo, seed_hi);
+              packed = P::pack(o);
+            }
+          }
+          st_vec<16>(out + static_cast<int64_t>(row) * ldo + static_cast<int64_t>(lane + j * 32) * V, packed);
         }
     }
   }
@@ -270,16 +282,14 @@ ce_bwd_kernel(const T* __restrict__ z, int64_t ld, const int64_t* __restrict__ l
 // ---------------------------------------------------------------------------------------------------------
 // Dropout with a counter-based generator: keep(i) is a pure function of (seed, element index), so the backward
 // regenerates the mask instead of storing it.  out = keep ? x / (1 - p) : 0.  16 random bits per element.
-__device__ __forceinline__ uint32_t mix32(uint32_t x) {       // lowbias32 finaliser
-  x ^= x >> 16; x *= 0x7feb352dU; x ^= x >> 15; x *= 0x846ca68bU; x ^= x >> 16;
-  return x;
-}
 template <typename T>
 __global__ void __launch_bounds__(256)
 dropout_kernel(const T* __restrict__ x, int64_t ldx, T* __restrict__ out, int64_t ldo, int n_rows, int nvec,
-               uint32_t thresh16, float scale, uint32_t seed_lo, uint32_t seed_hi, const uint32_t* __restrict__ step_dev) {
+               int64_t row0, DropArg drop) {
   using P = Pack<T, 16>;
-  if (step_dev != nullptr) seed_hi += 0x632be5abU * (*step_dev + 1u);   // device-side epoch counter (graph replay)
+  const uint32_t seed_hi = drop_seed_hi(drop);                         // device-side epoch counter (graph replay)
+  const uint32_t thresh16 = drop.thresh16, seed_lo = drop.seed_lo;
+  const float scale = drop.scale;
   constexpr int V = P::V;
   const int64_t total = static_cast<int64_t>(n_rows) * nvec;
   for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
@@ -287,13 +297,7 @@ dropout_kernel(const T* __restrict__ x, int64_t ldx, T* __restrict__ out, int64_
     const int r = static_cast<int>(i / nvec), vi = static_cast<int>(i % nvec);
     float f[V];
     P::unpack(*reinterpret_cast<const typename P::Raw*>(x + static_cast<int64_t>(r) * ldx + static_cast<int64_t>(vi) * V), f);
-    const uint32_t base = mix32(static_cast<uint32_t>(i) ^ seed_lo) ^ mix32(static_cast<uint32_t>(i >> 32) + seed_hi);
-#pragma unroll
-    for (int k = 0; k < V; k += 2) {
-      const uint32_t h = mix32(base + 0x9e3779b9U * (k / 2 + 1));
-      f[k] = ((h & 0xffffU) >= thresh16) ? f[k] * scale : 0.f;
-      if (k + 1 < V) f[k + 1] = ((h >> 16) >= thresh16) ? f[k + 1] * scale : 0.f;
-    }
+    drop_apply<V>(f, static_cast<uint64_t>(i) + static_cast<uint64_t>(row0) * nvec, thresh16, scale, seed_lo, seed_hi);
     st_vec<16>(out + static_cast<int64_t>(r) * ldo + static_cast<int64_t>(vi) * V, P::pack(f));
   }
 }
@@ -307,10 +311,10 @@ static int row_grid(int n_rows) {
 
 extern "C" int pg_row_grid(int32_t n_rows) { return pg::row_grid(n_rows); }
 
-extern "C" int pg_dropout(const void* x, int64_t ldx, void* out, int64_t ldo, int32_t n_rows, int32_t d, int dtype,
-                          float p, uint64_t seed, const uint32_t* step_dev, void* stream) {
+extern "C" int pg_dropout_rows(const void* x, int64_t ldx, void* out, int64_t ldo, int64_t row0, int32_t n_rows, int32_t d,
+                               int dtype, const pg_drop* drop, void* stream) {
   using namespace pg;
-  PG_REQUIRE(x && out && p >= 0.f && p < 1.f, "pg_dropout: bad argument");
+  PG_REQUIRE(x && out && drop && drop->p >= 0.f && drop->p < 1.f, "pg_dropout: bad argument");
   const int es = elem_size(dtype), v = 16 / es;
   PG_REQUIRE(d > 0 && round_up(d, v) <= ldx && round_up(d, v) <= ldo && vec_bytes(x, ldx, es) == 16 && vec_bytes(out, ldo, es) == 16,
              "pg_dropout: rows must be 16-byte aligned and padded to the vector width");
@@ -318,22 +322,37 @@ extern "C" int pg_dropout(const void* x, int64_t ldx, void* out, int64_t ldo, in
   const int64_t total = static_cast<int64_t>(n_rows) * nvec;
   if (total == 0) return PG_OK;
   const unsigned blocks = static_cast<unsigned>((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
-  const uint32_t thresh = static_cast<uint32_t>(p * 65536.0f + 0.5f);
-  const float scale = 1.0f / (1.0f - p);
+  DropArg a = make_drop(drop);
+  if (drop->p == 0.f) { a.thresh16 = 0u; a.scale = 1.f; }
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (dtype == PG_F32)
-    dropout_kernel<float><<<blocks, 256, 0, st>>>(static_cast<const float*>(x), ldx, static_cast<float*>(out), ldo, n_rows, nvec, thresh, scale, static_cast<uint32_t>(seed), static_cast<uint32_t>(seed >> 32), step_dev);
+    dropout_kernel<float><<<blocks, 256, 0, st>>>(static_cast<const float*>(x), ldx, static_cast<float*>(out), ldo, n_rows, nvec, row0, a);
   else
-    dropout_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(x), ldx, static_cast<__nv_bfloat16*>(out), ldo, n_rows, nvec, thresh, scale, static_cast<uint32_t>(seed), static_cast<uint32_t>(seed >> 32), step_dev);
+    dropout_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(x), ldx, static_cast<__nv_bfloat16*>(out), ldo, n_rows, nvec, row0, a);
   PG_LAUNCH_CHECK();
   return PG_OK;
+}
+
+extern "C" int pg_dropout(const void* x, int64_t ldx, void* out, int64_t ldo, int32_t n_rows, int32_t d, int dtype,
+                          float p, uint64_t seed, const uint32_t* step_dev, void* stream) {
+  pg_drop dr{p, seed, step_dev, 0};
+  return pg_dropout_rows(x, ldx, out, ldo, 0, n_rows, d, dtype, &dr, stream);
 }
 
 extern "C" int pg_ln_relu_fwd(const void* y, int64_t ldy, const float* gamma, const float* beta, float eps, int relu,
                               void* out, int64_t ldo, float* mean, float* rstd, int32_t n_rows, int32_t d, int dtype,
                               void* stream) {
+  return pg_ln_relu_drop_fwd(y, ldy, gamma, beta, eps, relu, out, ldo, nullptr, 0, mean, rstd, n_rows, d, dtype, nullptr, stream);
+}
+
+extern "C" int pg_ln_relu_drop_fwd(const void* y, int64_t ldy, const float* gamma, const float* beta, float eps, int relu,
+                                   void* out, int64_t ldo, void* out_clean, int64_t ldc, float* mean, float* rstd,
+                                   int32_t n_rows, int32_t d, int dtype, const pg_drop* drop, void* stream) {
   using namespace pg;
   PG_REQUIRE(y && gamma && beta && out && mean && rstd, "pg_ln_relu_fwd: null argument");
+  PG_REQUIRE(out_clean == nullptr || (ldc >= d && vec_bytes(out_clean, ldc, elem_size(dtype)) == 16),
+             "pg_ln_relu_drop_fwd: out_clean rows must be 16-byte aligned");
+  const DropArg da = make_drop(drop);
   const int v = 16 / elem_size(dtype);
   PG_REQUIRE(d > 0 && d % v == 0 && d / v <= 32 * kMaxVec, "pg_ln_relu_fwd: d=%d must be a multiple of %d and <= %d", d, v, 32 * kMaxVec * v);
   PG_REQUIRE(vec_bytes(y, ldy, elem_size(dtype)) == 16 && vec_bytes(out, ldo, elem_size(dtype)) == 16, "pg_ln_relu_fwd: rows must be 16-byte aligned");
@@ -341,7 +360,7 @@ extern "C" int pg_ln_relu_fwd(const void* y, int64_t ldy, const float* gamma, co
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int grid = row_grid(n_rows);
   const int vpl = (d / v + 31) / 32;
-#define PG_LNF(T_, VPL_, R_) ln_relu_fwd_kernel<T_, VPL_, R_><<<grid, kRowThreads, 0, st>>>(static_cast<const T_*>(y), ldy, gamma, beta, eps, relu, static_cast<T_*>(out), ldo, mean, rstd, n_rows, d)
+#define PG_LNF(T_, VPL_, R_) ln_relu_fwd_kernel<T_, VPL_, R_><<<grid, kRowThreads, 0, st>>>(static_cast<const T_*>(y), ldy, gamma, beta, eps, relu, static_cast<T_*>(out), ldo, mean, rstd, n_rows, d, static_cast<T_*>(out_clean), ldc, da)
   if (dtype == PG_F32) {
     if (vpl <= 1) PG_LNF(float, 1, 4); else if (vpl <= 2) PG_LNF(float, 2, 2); else PG_LNF(float, 4, 1);
   } else {

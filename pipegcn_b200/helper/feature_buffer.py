@@ -59,13 +59,13 @@ class _MsgSet:
 
 class _HaloUpdate(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, feat, buf, layer):
+    def forward(ctx, feat, buf, layer, push_src, drop):
         ctx.buf, ctx.layer, ctx.epoch = buf, layer, buf._epoch
-        return buf._forward(layer, feat)
+        return buf._forward(layer, feat, push_src, drop)
 
     @staticmethod
     def backward(ctx, grad):
-        return ctx.buf._backward(ctx.layer, ctx.epoch, grad), None, None
+        return ctx.buf._backward(ctx.layer, ctx.epoch, grad), None, None, None, None
 
 
 class Buffer(object):
@@ -238,7 +238,7 @@ class Buffer(object):
         self._self_msgs, self._fwd_msgs, self._bwd_msgs = {}, {}, {}
         for (l, v) in self._f_off:
             ld = self._ld[l]
-            m = _C.pg_msg(None, 0, self._num_in, 0, self._f_buf[(l, v)].data_ptr(), ld, None, 0, None, None)
+            m = _C.pg_msg(None, 0, self._num_in, 0, self._f_buf[(l, v)].data_ptr(), ld, None, 0, None, None, 0)
             self._self_msgs[(l, v)] = _MsgSet([m], dev)
             msgs = []
             for j in self._peers:
@@ -246,7 +246,7 @@ class Buffer(object):
                 ema = self._f_ema[l][j] if self._f_ema[l] is not None else None
                 msgs.append(_C.pg_msg(self._bidx[j].data_ptr(), 0, int(self._bidx[j].numel()), 0, dst, ld,
                                       ema.data_ptr() if ema is not None else None, ld,
-                                      flag_ptr(j, l, 0), counter_ptr()))
+                                      flag_ptr(j, l, 0), counter_ptr(), int(tables[j]['pl'][rank])))
             self._fwd_msgs[(l, v)] = _MsgSet(msgs, dev) if msgs else None
         for (l, v) in self._b_off:
             ld = self._ld[l]
@@ -256,7 +256,7 @@ class Buffer(object):
                 ema = self._b_ema[l][j] if self._b_ema[l] is not None else None
                 msgs.append(_C.pg_msg(None, self._pl[j], int(self._recv_shape[j]), 0, dst, ld,
                                       ema.data_ptr() if ema is not None else None, ld,
-                                      flag_ptr(j, l, 1), counter_ptr()))
+                                      flag_ptr(j, l, 1), counter_ptr(), int(tables[j]['boff'][rank])))
             self._bwd_msgs[(l, v)] = _MsgSet(msgs, dev) if msgs else None
         self._x0_msgs = None
         if self._static0:
@@ -269,7 +269,8 @@ class Buffer(object):
                 # the backward flag word of layer 0 is free (layer 0 has no gradient exchange): it carries the
                 # generation of the one-shot push
                 msgs.append(_C.pg_msg(self._bidx[j].data_ptr(), 0, int(self._bidx[j].numel()), 0, dst, ld,
-                                      None, 0, flag_ptr(j, 0, 1), counter_ptr()))
+                                      None, 0, flag_ptr(j, 0, 1), counter_ptr(),
+                                      int(tables[j]['pl'][rank] - tables[j]['num_in'])))
             self._x0_msgs = _MsgSet(msgs, dev) if msgs else None
         # device arrays of the flag words this rank waits on, per (layer, direction)
         self._wait = {}
@@ -294,6 +295,20 @@ class Buffer(object):
         if ev is not None:                       # the side-stream push of two epochs ago read these rows
             torch.cuda.current_stream().wait_event(ev)
         return self._f_buf[(layer, v)][:self._num_in, :self._layer_size[layer]]
+
+    def clean_view(self, layer):
+        """[N_in, d] buffer for the CLEAN (not dropped-out) rows of layer `layer` in this epoch's version: with the
+        dropout fused into the producers, `inner_view(layer)` holds dropout(h) for the local aggregate / GEMM and this
+        holds h itself -- what the halo push sends and what the LayerNorm backward needs."""
+        if not self._ready or (layer, 0) not in self._f_off:
+            return None
+        v = self._use_version()
+        if not hasattr(self, '_clean'):
+            self._clean = {}
+        if (layer, v) not in self._clean:
+            from ..graph import alloc_rows
+            self._clean[(layer, v)] = alloc_rows(self._num_in, self._layer_size[layer], self._dtype, self._world.device)
+        return self._clean[(layer, v)]
 
     def load_inner(self, layer, feat):
         """Write `feat` into the inner rows of every version of layer `layer` (static input features)."""
@@ -335,12 +350,18 @@ class Buffer(object):
                              f"[layer][fwd,bwd][source rank] = {self._flags.tolist()}")
 
     # ------------------------------------------------------------------ kernels
-    def _push(self, ms: Optional[_MsgSet], src: torch.Tensor, d: int, offset: int):
-        """`offset`: the flag carries epoch + offset (1 for a message of this epoch)."""
+    def _push(self, ms: Optional[_MsgSet], src: torch.Tensor, d: int, offset: int, drop=None):
+        """`offset`: the flag carries epoch + offset (1 for a message of this epoch).  `drop`: the RECEIVER's dropout
+        key, applied to the rows as they are stored into its buffer."""
         if ms is None:
             return
         value, value_dev = self._val(offset)
         _C.count(2)
+        if drop is not None and drop.p > 0:
+            _C.check(_C.lib.pg_halo_push_drop(ms.ptr, ms.n_msgs, ms.n_ctas, src.data_ptr(), src.stride(0), d,
+                                              _C.dtype_code(src.dtype), self._corr_momentum, 1 - self._corr_momentum,
+                                              value, value_dev, C.byref(drop.c()), _C.stream_ptr()), "pg_halo_push_drop")
+            return
         _C.check(_C.lib.pg_halo_push(ms.ptr, ms.n_msgs, ms.n_ctas, src.data_ptr(), src.stride(0), d,
                                      _C.dtype_code(src.dtype), self._corr_momentum, 1 - self._corr_momentum,
                                      value, value_dev, _C.stream_ptr()), "pg_halo_push")
@@ -439,27 +460,31 @@ class Buffer(object):
         return self._f_buf[(0, v)][:, :d]
 
     # ------------------------------------------------------------------ forward
-    def update(self, layer, feat):
-        """[N_in, d] -> [num_all, d] = cat(feat, halo rows of every peer); differentiable wrt feat."""
+    def update(self, layer, feat, push_src=None, drop=None):
+        """[N_in, d] -> [num_all, d] = cat(feat, halo rows of every peer); differentiable wrt feat.
+        Fused dropout (not in the reference): `feat` already holds dropout(h) under the key `drop`, `push_src` holds h;
+        the peers receive h with THEIR dropout of the same key applied by the push, so that the returned tensor is
+        dropout(cat(h, halo)) as model.py:47 would compute it -- without a pass over [num_all, d]."""
         self._check_feat(layer, feat)
         if not self._connected:
             self._connect()
-        return _HaloUpdate.apply(feat, self, layer)
+        return _HaloUpdate.apply(feat, self, layer, push_src, drop)
 
-    def _forward(self, layer, feat):
+    def _forward(self, layer, feat, push_src=None, drop=None):
         if layer == 0 and self._static0_ready:
             return self._forward_static0(feat)
         d = self._layer_size[layer]
         t = self._epoch
         if feat.stride(1) != 1:
             feat = feat.contiguous()
+        src = push_src if push_src is not None else feat      # what the peers receive (clean rows)
         def aliased(v):
             return feat.data_ptr() == self._f_buf[(layer, v)].data_ptr() and feat.stride(0) == self._ld[layer]
         if not self._pipeline:
             v = 0
             if not aliased(v):
                 self._push(self._self_msgs[(layer, v)], feat, d, 0)
-            self._push(self._fwd_msgs[(layer, v)], feat, d, 1)
+            self._push(self._fwd_msgs[(layer, v)], src, d, 1, drop)          # consumed in this epoch: same step
             self._wait_flags(layer, 0, 1, f'forward_{layer}')
         else:
             v_use, v_send = (t + 1) % 2, t % 2
@@ -475,10 +500,11 @@ class Buffer(object):
                 self._comm_stream.wait_stream(cur)
                 self._comm_forked = True
                 if not self.graph_mode:
-                    feat.record_stream(self._comm_stream)
-                self._keep.append(feat)
+                    src.record_stream(self._comm_stream)
+                self._keep.append(src)
                 with torch.cuda.stream(self._comm_stream):
-                    self._push(ms, feat, d, 1)
+                    # consumed by the peers in the NEXT epoch: their mask of step + 1
+                    self._push(ms, src, d, 1, drop.shifted(1) if drop is not None else None)
                     if zero_copy and not self.graph_mode:
                         ev = torch.cuda.Event()
                         ev.record()

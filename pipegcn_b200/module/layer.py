@@ -41,12 +41,14 @@ class GraphSAGELayer(nn.Module):
             if lin.bias is not None:
                 lin.bias.data.uniform_(-bound, bound)
 
-    def forward(self, graph, feat, in_deg):
+    def forward(self, graph, feat, in_deg, drop_bwd=None):
+        """`drop_bwd` (not in the reference): `feat` is already dropout(F) under that key -- the layer's gradient with
+        respect to F then includes the dropout backward (fused into the transposed aggregate's store)."""
         if self.training:
             if self.use_pp:
                 return ops.linear(feat, self.linear.weight, self.linear.bias)
             return ops.sage_layer(feat, graph, graph.deg_as_float(in_deg), self.linear1.weight, self.linear1.bias,
-                                  self.linear2.weight, self.linear2.bias)
+                                  self.linear2.weight, self.linear2.bias, drop_bwd)
         assert in_deg is None
         ah = ops.sage_aggregate(feat, graph, graph.row_degrees())
         if self.use_pp:

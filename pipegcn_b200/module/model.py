@@ -62,12 +62,24 @@ class GraphSAGE(GNNBase):
     def _buffer(self):
         return self.buffer if self.buffer is not None else ctx.buffer
 
-    def _norm_act(self, i, h, dest=None):
+    def _drop_spec(self, i):
+        """Dropout key of graph layer i in this epoch (same on every rank; the step is the buffer's device-side epoch)."""
+        from .. import ops
+        return ops.DropSpec(self.dropout.p, ops.layer_seed(i), getattr(self._buffer(), '_epoch_dev', None), 0)
+
+    def _norm_act(self, i, h, dest=None, fuse_drop=False):
         if self.use_norm:
             n = self.norm[i]
             from .. import ops
             if isinstance(n, nn.LayerNorm) and self.activation in (F.relu, torch.relu) and ops.ln_relu_supported(h):
                 # LayerNorm + ReLU in one pass, written straight into the next layer's exchange buffer
+                if fuse_drop and dest is not None:
+                    clean = self._buffer().clean_view(i + 1)
+                    if clean is not None and ops._drop_ok(dest) and ops._drop_ok(clean):
+                        # ... together with the NEXT layer's dropout: dest <- dropout(h), clean <- h
+                        self._fused = (i + 1, clean)
+                        return ops.layer_norm_relu(h, n.weight, n.bias, n.eps, relu=True, out=dest, clean=clean,
+                                                   drop=self._drop_spec(i + 1))
                 return ops.layer_norm_relu(h, n.weight, n.bias, n.eps, relu=True, out=dest)
             if isinstance(n, nn.LayerNorm) and h.dtype != n.weight.dtype:
                 h = F.layer_norm(h, n.normalized_shape, n.weight.to(h.dtype), n.bias.to(h.dtype), n.eps)
@@ -76,20 +88,32 @@ class GraphSAGE(GNNBase):
         return self.activation(h)
 
     def forward(self, g, feat, in_deg=None):
+        from .. import ops
         h = feat if feat.dtype == self.act_dtype else feat.to(self.act_dtype)
+        p = self.dropout.p if self.training else 0.0
+        self._fused = None
         for i, layer in enumerate(self.layers):
             if i < self.n_graph_layers:
+                fused = self._fused is not None and self._fused[0] == i
                 if self.training and (i > 0 or not self.use_pp):
-                    h = self._buffer().update(i, h)
-                h = layer(g, self._drop(h), in_deg)
+                    if fused:       # h = dropout(LayerNorm output), written by the epilogue; the peers get the clean rows
+                        h = self._buffer().update(i, h, push_src=self._fused[1], drop=self._drop_spec(i))
+                    else:
+                        h = self._buffer().update(i, h)
+                if fused:
+                    h = layer(g, h, in_deg, drop_bwd=self._drop_spec(i))
+                elif self.training and p > 0 and i > 0 and ops._drop_ok(h):
+                    # same mask as the fused path, as separate passes (PG_FUSED_DROPOUT=0 / unsupported shapes)
+                    h = layer(g, ops.keyed_dropout(h, self._drop_spec(i)), in_deg)
+                else:
+                    h = layer(g, self._drop(h), in_deg)
             else:
-                from .. import ops
                 h = ops.linear(self._drop(h), layer.weight, layer.bias)
             if i < self.n_layers - 1:
                 dest = None
                 if self.training and i + 1 < self.n_graph_layers:
                     dest = self._buffer().inner_view(i + 1)
-                h = self._norm_act(i, h, dest)
+                h = self._norm_act(i, h, dest, fuse_drop=ops.FUSED_DROPOUT and p > 0 and dest is not None)
         return h
 
 

@@ -23,9 +23,46 @@ def _rows(t: torch.Tensor):
     return t
 
 
+class DropSpec:
+    """Key of a dropout mask (include/pipegcn_b200.h: pg_drop): probability, 64-bit seed, device-side step counter +
+    offset.  The same key evaluated by different kernels gives the same mask, so the mask is never stored."""
+
+    def __init__(self, p: float, seed: int, step: torch.Tensor = None, step_off: int = 0):
+        self.p, self.seed, self.step, self.step_off = float(p), int(seed) & 0xFFFFFFFFFFFFFFFF, step, int(step_off)
+
+    def shifted(self, off: int) -> "DropSpec":
+        return DropSpec(self.p, self.seed, self.step, self.step_off + off)
+
+    def c(self):
+        return _C.pg_drop(self.p, self.seed, self.step.data_ptr() if self.step is not None else None, self.step_off)
+
+
+def layer_seed(layer: int) -> int:
+    """Dropout seed of graph layer `layer`: the same on every rank (all ranks seed torch identically, train.py:298)."""
+    return (torch.initial_seed() * 0x9E3779B97F4A7C15 + (layer + 1) * 0xD1B54A32D192ED03) & 0xFFFFFFFFFFFFFFFF
+
+
+def _drop_ok(t: torch.Tensor) -> bool:
+    """The mask is defined on 16-byte vectors of padded, aligned rows."""
+    return t.dim() == 2 and t.is_cuda and t.stride(1) == 1 and (t.stride(0) * t.element_size()) % 16 == 0 \
+        and t.data_ptr() % 16 == 0 and t.stride(0) >= (t.shape[1] + 7) // 8 * 8 and t.dtype in (torch.float32, torch.bfloat16)
+
+
+def dropout_rows(x: torch.Tensor, spec: DropSpec, out: torch.Tensor = None, row0: int = 0) -> torch.Tensor:
+    """out = dropout(x) under the key `spec`; rows are numbered from row0 (x may be a row slice of a larger tensor)."""
+    if out is None:
+        out = alloc_rows(x.shape[0], x.shape[1], x.dtype, x.device)
+    _C.count()
+    _C.check(_C.lib.pg_dropout_rows(x.data_ptr(), x.stride(0), out.data_ptr(), out.stride(0), int(row0), x.shape[0],
+                                    x.shape[1], _C.dtype_code(x.dtype), C.byref(spec.c()), _C.stream_ptr()),
+             "pg_dropout_rows")
+    return out
+
+
 def aggregate(plan: CsrPlan, x: torch.Tensor, out: torch.Tensor = None, row_div: torch.Tensor = None,
-              acc_rows: int = 0) -> torch.Tensor:
-    """out[r] = sum_{e in row r} x[indices[e]] (/ row_div[r]) (+ out[r] for r < acc_rows)."""
+              acc_rows: int = 0, drop: DropSpec = None) -> torch.Tensor:
+    """out[r] = sum_{e in row r} x[indices[e]] (/ row_div[r]) (+ out[r] for r < acc_rows); with `drop` the mask of that
+    key is applied to every row as it is written."""
     _rows(x)
     d = x.shape[1]
     if out is None:
@@ -38,10 +75,16 @@ def aggregate(plan: CsrPlan, x: torch.Tensor, out: torch.Tensor = None, row_div:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
     _C.count(2 if plan.n_long else 1)
-    _C.check(_C.lib.pg_aggregate(C.byref(plan.c), x.data_ptr(), x.stride(0), out.data_ptr(), out.stride(0), d,
-                                 _C.dtype_code(x.dtype), row_div.data_ptr() if row_div is not None else None,
-                                 int(acc_rows), scratch.data_ptr() if scratch is not None else None,
-                                 _C.stream_ptr()), "pg_aggregate")
+    if drop is not None and drop.p > 0:
+        _C.check(_C.lib.pg_aggregate_drop(C.byref(plan.c), x.data_ptr(), x.stride(0), out.data_ptr(), out.stride(0), d,
+                                          _C.dtype_code(x.dtype), row_div.data_ptr() if row_div is not None else None,
+                                          int(acc_rows), scratch.data_ptr() if scratch is not None else None,
+                                          C.byref(drop.c()), _C.stream_ptr()), "pg_aggregate_drop")
+    else:
+        _C.check(_C.lib.pg_aggregate(C.byref(plan.c), x.data_ptr(), x.stride(0), out.data_ptr(), out.stride(0), d,
+                                     _C.dtype_code(x.dtype), row_div.data_ptr() if row_div is not None else None,
+                                     int(acc_rows), scratch.data_ptr() if scratch is not None else None,
+                                     _C.stream_ptr()), "pg_aggregate")
     if prof is not None:
         e1.record()
         prof.append((e0, e1, aggregate_bytes(plan, x, row_div is not None)))
@@ -297,7 +340,10 @@ class SageLayerFn(torch.autograd.Function):
     """
 
     @staticmethod
-    def forward(ctx, feat, graph, deg_f, w1, b1, w2, b2):
+    def forward(ctx, feat, graph, deg_f, w1, b1, w2, b2, drop_bwd=None):
+        # drop_bwd: `feat` already IS dropout(F) (written that way by its producers); the gradient returned is the one
+        # with respect to F, i.e. the dropout backward is applied to g_feat as the transposed aggregate writes it
+        ctx.drop_bwd = drop_bwd
         if feat.stride(1) != 1:
             feat = feat.contiguous()
         n_in = graph.num_in
@@ -326,11 +372,11 @@ class SageLayerFn(torch.autograd.Function):
             g_feat = alloc_rows(ctx.num_all, d_in, x.dtype, x.device)
             gemm_nt(gsp, padded_weight(w1, x.dtype, transpose=True), out=g_feat[:graph.num_in])
             gs = gemm_nt(gsp, padded_weight(w2, x.dtype, transpose=True), row_div=deg_f)
-            aggregate(graph.bwd, gs, out=g_feat, acc_rows=graph.num_in)
+            aggregate(graph.bwd, gs, out=g_feat, acc_rows=graph.num_in, drop=ctx.drop_bwd)
         gw1 = wgrad(gsp, x).to(w1.dtype)
         gw2 = wgrad(gsp, ah).to(w2.dtype)
         gb = (colsum if colsum is not None else g.float().sum(0)) if ctx.has_bias else None
-        return g_feat, None, None, gw1, gb, gw2, gb
+        return g_feat, None, None, gw1, gb, gw2, gb, None
 
 
 class SageLayerNarrowFn(torch.autograd.Function):
@@ -348,7 +394,8 @@ class SageLayerNarrowFn(torch.autograd.Function):
     """
 
     @staticmethod
-    def forward(ctx, feat, graph, deg_f, w1, b1, w2, b2):
+    def forward(ctx, feat, graph, deg_f, w1, b1, w2, b2, drop_bwd=None):
+        ctx.drop_bwd = drop_bwd
         if feat.stride(1) != 1:
             feat = feat.contiguous()
         n_in = graph.num_in
@@ -382,20 +429,22 @@ class SageLayerNarrowFn(torch.autograd.Function):
             gemm_nt(dzsp.rows(0, n_in) if is_split else dz[:n_in], w2t, gsp, w1t, out=g_feat[:n_in])
             if feat.shape[0] > n_in:
                 gemm_nt(dzsp.rows(n_in) if is_split else dz[n_in:], w2t, out=g_feat[n_in:])
+            if ctx.drop_bwd is not None and ctx.drop_bwd.p > 0:       # g_feat comes out of a GEMM here: one pass
+                dropout_rows(g_feat, ctx.drop_bwd, out=g_feat)
         gw1 = wgrad(gsp, fsp.rows(0, n_in) if is_split else feat[:n_in]).to(w1.dtype)
         gw2 = wgrad(dzsp, fsp).to(w2.dtype)
         gb = (colsum if colsum is not None else g.float().sum(0)) if ctx.has_bias else None
-        return g_feat, None, None, gw1, gb, gw2, gb
+        return g_feat, None, None, gw1, gb, gw2, gb, None
 
 
 # transform-first when the layer narrows (PG_NARROW=0 keeps the reference's aggregate-first association everywhere)
 NARROW = os.environ.get("PG_NARROW", "1") != "0"
 
 
-def sage_layer(feat, graph, deg_f, w1, b1, w2, b2) -> torch.Tensor:
+def sage_layer(feat, graph, deg_f, w1, b1, w2, b2, drop_bwd=None) -> torch.Tensor:
     if NARROW and w1.shape[0] < feat.shape[1]:
-        return SageLayerNarrowFn.apply(feat, graph, deg_f, w1, b1, w2, b2)
-    return SageLayerFn.apply(feat, graph, deg_f, w1, b1, w2, b2)
+        return SageLayerNarrowFn.apply(feat, graph, deg_f, w1, b1, w2, b2, drop_bwd)
+    return SageLayerFn.apply(feat, graph, deg_f, w1, b1, w2, b2, drop_bwd)
 
 
 def sage_linear(x, ah, w1, b1, w2, b2) -> torch.Tensor:
@@ -437,7 +486,9 @@ class LayerNormReLU(torch.autograd.Function):
     sums of g_y, which is the bias gradient of the linear that produced y."""
 
     @staticmethod
-    def forward(ctx, y, gamma, beta, eps, relu, out):
+    def forward(ctx, y, gamma, beta, eps, relu, out, clean=None, drop=None):
+        # clean / drop: `out` receives dropout(result) under the key `drop` (the next layer's dropout, fused), `clean`
+        # the result itself (source of the halo push, ReLU mask of the backward)
         n, d = y.shape
         if out is None:
             out = alloc_rows(n, d, y.dtype, y.device)
@@ -445,10 +496,17 @@ class LayerNormReLU(torch.autograd.Function):
         rstd = torch.empty(n, dtype=torch.float32, device=y.device)
         g32, b32 = gamma.detach().float().contiguous(), beta.detach().float().contiguous()
         _C.count()
-        _C.check(_C.lib.pg_ln_relu_fwd(y.data_ptr(), y.stride(0), g32.data_ptr(), b32.data_ptr(), float(eps), int(relu),
-                                       out.data_ptr(), out.stride(0), mean.data_ptr(), rstd.data_ptr(), n, d,
-                                       _C.dtype_code(y.dtype), _C.stream_ptr()), "pg_ln_relu_fwd")
-        ctx.save_for_backward(y, out, mean, rstd, g32)
+        if clean is not None:
+            _C.check(_C.lib.pg_ln_relu_drop_fwd(y.data_ptr(), y.stride(0), g32.data_ptr(), b32.data_ptr(), float(eps),
+                                                int(relu), out.data_ptr(), out.stride(0), clean.data_ptr(), clean.stride(0),
+                                                mean.data_ptr(), rstd.data_ptr(), n, d, _C.dtype_code(y.dtype),
+                                                C.byref(drop.c()) if drop is not None else None, _C.stream_ptr()),
+                     "pg_ln_relu_drop_fwd")
+        else:
+            _C.check(_C.lib.pg_ln_relu_fwd(y.data_ptr(), y.stride(0), g32.data_ptr(), b32.data_ptr(), float(eps), int(relu),
+                                           out.data_ptr(), out.stride(0), mean.data_ptr(), rstd.data_ptr(), n, d,
+                                           _C.dtype_code(y.dtype), _C.stream_ptr()), "pg_ln_relu_fwd")
+        ctx.save_for_backward(y, clean if clean is not None else out, mean, rstd, g32)
         ctx.relu = bool(relu)
         ctx.param_dtype = gamma.dtype
         return out
@@ -470,11 +528,38 @@ class LayerNormReLU(torch.autograd.Function):
                                        red[2].data_ptr(), partial.data_ptr(), n, d, _C.dtype_code(y.dtype),
                                        _C.stream_ptr()), "pg_ln_relu_bwd")
         _stash_colsum(g_y, red[2])
-        return g_y, red[0].to(ctx.param_dtype), red[1].to(ctx.param_dtype), None, None, None
+        return g_y, red[0].to(ctx.param_dtype), red[1].to(ctx.param_dtype), None, None, None, None, None
 
 
-def layer_norm_relu(y, gamma, beta, eps=1e-5, relu=True, out=None):
-    return LayerNormReLU.apply(y, gamma, beta, eps, relu, out)
+def layer_norm_relu(y, gamma, beta, eps=1e-5, relu=True, out=None, clean=None, drop=None):
+    return LayerNormReLU.apply(y, gamma, beta, eps, relu, out, clean, drop)
+
+
+class KeyedDropout(torch.autograd.Function):
+    """dropout(x) under an explicit key, forward and backward (the un-fused form of what the fused producers do:
+    PG_FUSED_DROPOUT=0, and the reference the fused kernels are tested against)."""
+
+    @staticmethod
+    def forward(ctx, x, spec):
+        ctx.spec = spec
+        return dropout_rows(x, spec)
+
+    @staticmethod
+    def backward(ctx, g):
+        if not _drop_ok(g):
+            gp = alloc_rows(g.shape[0], g.shape[1], g.dtype, g.device)
+            gp.copy_(g)
+            g = gp
+        return dropout_rows(g, ctx.spec, out=g), None
+
+
+def keyed_dropout(x, spec: DropSpec):
+    return KeyedDropout.apply(x, spec) if spec.p > 0 else x
+
+
+# dropout of graph layers >= 1 applied by the producers of the dropped tensor (LayerNorm epilogue, halo push,
+# transposed aggregate) instead of by [num_all, d] passes; PG_FUSED_DROPOUT=0: the same masks by separate passes
+FUSED_DROPOUT = os.environ.get("PG_FUSED_DROPOUT", "1") != "0"
 
 
 class CrossEntropySum(torch.autograd.Function):

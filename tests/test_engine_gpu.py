@@ -216,3 +216,64 @@ def test_engine_with_empty_messages(mode):
         for r, eng in enumerate(trainer.engines):
             torch.testing.assert_close(eng.last_logits.cpu(), traces[r].logits[e], rtol=2e-4, atol=2e-4)
             assert abs(float(losses[r].item()) - traces[r].losses[e]) <= 1e-4 * abs(traces[r].losses[e]) + 1e-5
+
+
+@pytest.mark.parametrize("dtype", ["fp32", "bf16"])
+@pytest.mark.parametrize("mode", ["sync_corr", "pipeline_corr"])
+def test_fused_dropout_equals_separate_passes(mode, dtype):
+    """--dropout 0.5: the masks applied by the producers (LayerNorm epilogue, halo push with the receiver's key, transposed
+    aggregate / GEMM output) are the masks separate [num_all, d] passes would apply under the same keys: logits and
+    losses are bit-identical, gradients identical in fp32 (bf16: the fused store rounds once instead of twice)."""
+    from pipegcn_b200 import ops
+    from pipegcn_b200.train import LocalTrainer
+    from pipegcn_b200.world import LocalWorld
+    from tests.helpers import make_args, small_world
+    g, _, layouts, _ = small_world("small", 3)
+    outs = []
+    saved = ops.FUSED_DROPOUT
+    try:
+        for fused in (True, False):
+            ops.FUSED_DROPOUT = fused
+            torch.manual_seed(123)
+            _, eargs = make_args(g, 16, n_epochs=3, n_hidden=64, dropout=0.5, **MODES[mode])
+            eargs.dtype = dtype
+            trainer = LocalTrainer(layouts, eargs, LocalWorld(3, "cuda"))
+            ep = []
+            for _ in range(3):
+                losses = trainer.run_epoch(keep_logits=True)
+                ep.append(([float(l.item()) for l in losses], [e.last_logits.float().clone() for e in trainer.engines],
+                           [[p.grad.detach().float().clone() for p in e.model.parameters()] for e in trainer.engines]))
+            outs.append(ep)
+    finally:
+        ops.FUSED_DROPOUT = saved
+    zero_frac = (outs[0][0][1][0] == 0).float().mean().item()
+    assert zero_frac < 0.2          # logits are not dropped; the hidden activations were (next assert needs p > 0 to bite)
+    for (la, za, ga), (lb, zb, gb) in zip(*outs):
+        assert la == lb
+        for a, b in zip(za, zb):
+            assert torch.equal(a, b)
+        for ra, rb in zip(ga, gb):
+            for a, b in zip(ra, rb):
+                if dtype == "fp32":
+                    torch.testing.assert_close(a, b, rtol=1e-6, atol=1e-9)
+                else:
+                    torch.testing.assert_close(a, b, rtol=5e-2, atol=2e-2 * max(b.abs().max().item(), 1e-6))
+
+
+def test_keyed_dropout_statistics_and_row_offset():
+    """pg_dropout_rows: the kept fraction is 1 - p, kept values are scaled by 1 / (1 - p), the mask of a row slice equals
+    the slice of the mask (row0), and it changes with the step counter."""
+    from pipegcn_b200 import ops
+    from pipegcn_b200.graph import alloc_rows
+    x = alloc_rows(4096, 256, torch.float32, "cuda")
+    x.fill_(1.0)
+    step = torch.zeros(1, dtype=torch.int32, device="cuda")
+    spec = ops.DropSpec(0.3, 12345, step, 0)
+    y = ops.dropout_rows(x, spec)
+    kept = (y != 0).float().mean().item()
+    assert abs(kept - 0.7) < 0.01 and torch.allclose(y[y != 0], torch.tensor(1 / 0.7, device="cuda"))
+    part = ops.dropout_rows(x[1000:1500], spec, row0=1000)
+    assert torch.equal(part, y[1000:1500])
+    step.add_(1)
+    assert not torch.equal(ops.dropout_rows(x, spec), y)
+    assert torch.equal(ops.dropout_rows(x, spec.shifted(-1)), y)
