@@ -133,6 +133,11 @@ typedef struct pg_gemm_src {
 
 int pg_linear(int dtype_in, int dtype_out, const pg_gemm_src* srcs, int32_t n_src, const float* bias,
               const float* row_div, void* c, int64_t ldc, int32_t m, int32_t n, void* stream);
+/* the same with the dropout mask of `drop` applied to c as it is written; c's row 0 is row drop_row0 of the tensor the
+ * mask is defined on (the gradient of a dropped tensor produced by a GEMM: transform-first layers) */
+int pg_linear_drop(int dtype_in, int dtype_out, const pg_gemm_src* srcs, int32_t n_src, const float* bias,
+                   const float* row_div, void* c, int64_t ldc, int32_t m, int32_t n, const pg_drop* drop,
+                   int64_t drop_row0, void* stream);
 
 /*
  * Weight gradients on the tcgen05 tensor cores (MN-major operands, split-K over the rows, deterministic):

@@ -58,6 +58,8 @@ def _load():
                                         C.POINTER(pg_drop), vp]),
         "pg_row_div": (C.c_int, [vp, i64, vp, i64, i32, i32, C.c_int, vp, vp]),
         "pg_linear": (C.c_int, [C.c_int, C.c_int, C.POINTER(pg_gemm_src), i32, vp, vp, vp, i64, i32, i32, vp]),
+        "pg_linear_drop": (C.c_int, [C.c_int, C.c_int, C.POINTER(pg_gemm_src), i32, vp, vp, vp, i64, i32, i32,
+                                     C.POINTER(pg_drop), i64, vp]),
         "pg_wgrad_workspace": (i64, [i32, i32, i32, C.c_int]),
         "pg_wgrad": (C.c_int, [C.c_int, C.POINTER(pg_gemm_src), i32, vp, i64, i32, i32, i32, vp, i64, vp]),
         "pg_split_tf32": (C.c_int, [vp, i64, vp, vp, i64, i32, i32, vp]),
@@ -95,7 +97,8 @@ def _load():
 lib, EXPORTS = _load()
 for _k, _v in (("agg_unroll", os.environ.get("PG_AGG_UNROLL")), ("agg_pack_short", os.environ.get("PG_AGG_PACK")),
                ("agg_impl", os.environ.get("PG_AGG_IMPL")), ("agg_l2_hint", os.environ.get("PG_AGG_L2_HINT")),
-               ("agg_occ", os.environ.get("PG_AGG_OCC")), ("agg_overlap", os.environ.get("PG_AGG_OVERLAP"))):
+               ("agg_occ", os.environ.get("PG_AGG_OCC")), ("agg_overlap", os.environ.get("PG_AGG_OVERLAP")),
+               ("agg_narrow", os.environ.get("PG_AGG_NARROW"))):
     if _v:
         lib.pg_set_option(_k.encode(), int(_v))
 

@@ -190,6 +190,7 @@ agg_fixup_kernel(pg_csr g, T* __restrict__ out, int64_t ldo, int nvec, const flo
   }
 }
 
+int g_agg_narrow = 1;  // pg_set_option("agg_narrow", 0|1): chunked sub-warp kernels for rows of at most 16 vectors
 int g_agg_overlap = 1; // pg_set_option("agg_overlap", 0|1): short-row kernel on a side stream next to the long-row kernel
 int g_agg_impl = 2;     // pg_set_option("agg_impl", 1|2|3): 1 = row-per-group kernel, 2 = chunked kernels (need pg_csr::chunks),
                         // 3 = chunked, long rows staged through shared memory with cp.async
@@ -576,6 +577,207 @@ agg2_small_kernel(pg_csr g, const T* __restrict__ x, uint32_t ldx_bytes, T* __re
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Narrow rows (at most 16 vectors of 16 bytes: the d_out-wide aggregates of transform-first layers, class-wide
+// rows).  G = 4 / 8 / 16 lanes cover one row, so a warp fetches R = 32 / G neighbour rows per load instruction:
+//   long rows / segments : lane group q takes the entries q, q + R, q + 2R, ... of the row; the R partial sums are
+//                          added with xor-shuffles at the end (fixed order)
+//   chunks of short rows : lane group q takes the rows q, q + R, ... of the chunk; all groups walk rows of the same
+//                          length, so the flush points are warp-uniform and only the stores are predicated
+// Same chunk plan, same coalesced index loads + shuffles as the full-width kernels.
+template <typename T, int VB, int G>
+struct AggN {
+  using P = Pack<T, VB>;
+  using Raw = typename P::Raw;
+  static constexpr int V = P::V;
+  static constexpr int NA = P::NA;
+  static constexpr int R = 32 / G;
+  static constexpr int U = 8;
+  static constexpr unsigned kFull = 0xffffffffu;
+  const char* xc;           // this lane's column of source row 0
+  bool act;                 // lane's column exists
+  uint32_t ldx_bytes;
+  T* out;
+  int64_t ldo;
+  int col, q, acc_rows, nvec;
+  DropArg drop;
+  uint32_t drop_hi;
+  float2 acc[NA];
+
+  __device__ __forceinline__ void zero() {
+#pragma unroll
+    for (int i = 0; i < NA; ++i) acc[i] = make_float2(0.f, 0.f);
+  }
+  __device__ __forceinline__ Raw ld_row(uint32_t s) const {
+    return ld_vec<VB>(xc + static_cast<uint64_t>(s & 0x7fffffffu) * ldx_bytes);
+  }
+  __device__ __forceinline__ void add_masked(Raw t, bool keep) {
+    const uint32_t m = keep ? 0xffffffffu : 0u;
+    uint32_t* w = reinterpret_cast<uint32_t*>(&t);
+#pragma unroll
+    for (int i = 0; i < VB / 4; ++i) w[i] &= m;
+    P::add(acc, t);
+  }
+  __device__ __forceinline__ void store(int row, float inv, bool valid) {
+    if (valid && act) {
+      T* op = out + static_cast<int64_t>(row) * ldo + static_cast<int64_t>(col) * V;
+      float r[V];
+#pragma unroll
+      for (int i = 0; i < V; ++i) r[i] = ((i & 1) ? acc[i / 2].y : acc[i / 2].x) * inv;
+      if (row < acc_rows) {
+        float ov[V];
+        P::unpack(*reinterpret_cast<const Raw*>(op), ov);
+#pragma unroll
+        for (int i = 0; i < V; ++i) r[i] += ov[i];
+      }
+      if (drop.thresh16 != 0u)
+        drop_apply<V>(r, static_cast<uint64_t>(row) * nvec + col, drop.thresh16, drop.scale, drop.seed_lo, drop_hi);
+      st_vec<VB>(op, P::pack(r));
+    }
+    zero();
+  }
+  // sum of the R group partials into every lane (xor butterflies: the same order on every lane)
+  __device__ __forceinline__ void reduce_groups() {
+#pragma unroll
+    for (int off = G; off < 32; off <<= 1)
+#pragma unroll
+      for (int i = 0; i < NA; ++i) {
+        acc[i].x += __shfl_xor_sync(kFull, acc[i].x, off);
+        acc[i].y += __shfl_xor_sync(kFull, acc[i].y, off);
+      }
+  }
+};
+
+template <typename A, typename T>
+__device__ __forceinline__ void aggn_setup(A& a, const T* x, uint32_t ldx_bytes, T* out, int64_t ldo, int acc_rows, int nvec,
+                                           const DropArg& drop, int lane) {
+  constexpr int G = 32 / A::R;
+  a.col = lane % G;
+  a.q = lane / G;
+  a.act = a.col < nvec;
+  a.xc = reinterpret_cast<const char*>(x + static_cast<int64_t>(a.act ? a.col : 0) * A::V);
+  a.ldx_bytes = ldx_bytes;
+  a.out = out;
+  a.ldo = ldo;
+  a.acc_rows = acc_rows;
+  a.nvec = nvec;
+  a.drop = drop;
+  a.drop_hi = drop_seed_hi(drop);
+  a.zero();
+}
+
+template <typename T, int VB, int G>
+__global__ void __launch_bounds__(256, 4)
+aggn_long_kernel(pg_csr g, const T* __restrict__ x, uint32_t ldx_bytes, T* __restrict__ out, int64_t ldo, int nvec,
+                 const float* __restrict__ row_div, int acc_rows, float* __restrict__ scratch, int64_t lds, DropArg drop) {
+  using A = AggN<T, VB, G>;
+  using Raw = typename A::Raw;
+  constexpr int V = A::V, R = A::R, U = A::U;
+  constexpr unsigned kFull = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
+  const int cid = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (cid >= g.n_chunks_long) return;
+  const int4 c = __ldcs(reinterpret_cast<const int4*>(g.chunks) + cid);
+  const uint32_t* __restrict__ pidx = reinterpret_cast<const uint32_t*>(g.pidx) + c.x;
+  const int n_e = c.y;
+  A a;
+  aggn_setup(a, x, ldx_bytes, out, ldo, acc_rows, nvec, drop, lane);
+  uint32_t nxt = lane < n_e ? __ldcs(pidx + lane) : 0u;
+#pragma unroll 1
+  for (int base = 0; base < n_e; base += 32) {
+    const uint32_t my_idx = nxt;                          // lanes past the end hold column 0: a valid row
+    if (base + 32 + lane < n_e) nxt = __ldcs(pidx + base + 32 + lane);
+    const int n = min(32, n_e - base);
+    // step u of this block: group q fetches entry u * R + q
+#pragma unroll 1
+    for (int u0 = 0; u0 * R < n; u0 += U) {
+      Raw v[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) v[u] = a.ld_row(__shfl_sync(kFull, my_idx, ((u0 + u) * R + a.q) & 31));
+      if (n == 32 && (u0 + U) * R <= 32) {
+#pragma unroll
+        for (int u = 0; u < U; ++u) A::P::add(a.acc, v[u]);
+      } else {
+#pragma unroll
+        for (int u = 0; u < U; ++u) a.add_masked(v[u], (u0 + u) * R + a.q < n);
+      }
+    }
+  }
+  a.reduce_groups();
+  if ((c.w & 3) == 2) {
+    if (a.q == 0 && a.act) {
+      float* sp = scratch + static_cast<int64_t>(c.z) * lds + static_cast<int64_t>(a.col) * V;
+#pragma unroll
+      for (int i = 0; i < V; ++i) sp[i] = (i & 1) ? a.acc[i / 2].y : a.acc[i / 2].x;
+    }
+  } else {
+    const int row = __ldg(g.prow + c.z);
+    a.store(row, row_div != nullptr ? 1.f / __ldg(row_div + row) : 1.f, a.q == 0);
+  }
+}
+
+template <typename T, int VB, int G>
+__global__ void __launch_bounds__(256, 4)
+aggn_small_kernel(pg_csr g, const T* __restrict__ x, uint32_t ldx_bytes, T* __restrict__ out, int64_t ldo, int nvec,
+                  const float* __restrict__ row_div, int acc_rows, DropArg drop) {
+  using A = AggN<T, VB, G>;
+  using Raw = typename A::Raw;
+  constexpr int R = A::R, U = A::U;
+  constexpr unsigned kFull = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
+  const int cid = g.n_chunks_long + blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (cid >= g.n_chunks) return;
+  const int4 c = __ldcs(reinterpret_cast<const int4*>(g.chunks) + cid);
+  const int n_rows = c.w >> 2, len = c.y, n_e = len * n_rows;
+  const uint32_t my_idx = lane < n_e ? __ldcs(reinterpret_cast<const uint32_t*>(g.pidx) + c.x + lane) : 0u;
+  int my_row = 0;
+  float my_inv = 1.f;
+  if (lane < n_rows) {
+    my_row = __ldg(g.prow + c.z + lane);
+    if (row_div != nullptr) my_inv = 1.f / __ldg(row_div + my_row);
+  }
+  A a;
+  aggn_setup(a, x, ldx_bytes, out, ldo, acc_rows, nvec, drop, lane);
+  // group q walks the rows q, q + R, ...: T rows of `len` entries each, the same positions in every group
+  const int t_rows = (n_rows + R - 1) / R;
+  if (len == 0) {
+    for (int t = 0; t < t_rows; ++t) {
+      const int rq = t * R + a.q;
+      a.store(__shfl_sync(kFull, my_row, rq & 31), 1.f, rq < n_rows);
+    }
+    return;
+  }
+  const int n_pos = t_rows * len;
+  int t_ld = 0, k_ld = 0;                                 // (row-in-group, entry) of the next position to fetch
+  int t_add = 0, k_add = 0;
+#pragma unroll 1
+  for (int p0 = 0; p0 < n_pos; p0 += U) {
+    Raw v[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int rq = t_ld * R + a.q;
+      v[u] = a.ld_row(__shfl_sync(kFull, my_idx, (rq * len + k_ld) & 31));      // lanes >= n_e hold column 0
+      if (++k_ld == len) { k_ld = 0; ++t_ld; }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      if (p0 + u < n_pos) {                                 // warp-uniform
+        const int rq = t_add * R + a.q;
+        a.add_masked(v[u], rq < n_rows);
+        if (++k_add == len) {
+          a.store(__shfl_sync(kFull, my_row, rq & 31), __shfl_sync(kFull, my_inv, rq & 31), rq < n_rows);
+          k_add = 0;
+          ++t_add;
+        }
+      }
+    }
+  }
+}
+
+template <typename T, int VB, int G>
+static int launch_aggn(const pg_csr& g, const T* x, int64_t ldx, T* out, int64_t ldo, int nvec, const float* row_div,
+                       int acc_rows, float* scratch, int64_t lds, const DropArg& da, cudaStream_t st);
+
 // The long-row kernel is bound by instruction issue and L2 bandwidth, the short-row kernel by DRAM latency (it
 // touches the cold sources and writes most of the output): they run side by side, the short rows on a side stream
 // forked from and joined to the caller's stream with events (legal inside a CUDA-graph capture).
@@ -644,6 +846,36 @@ static int launch_agg2h(const pg_csr& g, const T* x, int64_t ldx, T* out, int64_
   return PG_OK;
 }
 
+template <typename T, int VB, int G>
+static int launch_aggn(const pg_csr& g, const T* x, int64_t ldx, T* out, int64_t ldo, int nvec, const float* row_div,
+                       int acc_rows, float* scratch, int64_t lds, const DropArg& da, cudaStream_t st) {
+  const uint32_t ldxb = static_cast<uint32_t>(ldx * sizeof(T));
+  AggSide* side = nullptr;
+  if (g.n_chunks > g.n_chunks_long) {
+    const unsigned blocks = static_cast<unsigned>((g.n_chunks - g.n_chunks_long + 7) / 8);
+    cudaStream_t ss = st;
+    if (g_agg_overlap && g.n_chunks_long > 0 && (side = agg_side_for(st)) != nullptr) {
+      PG_CHECK_CUDA(cudaEventRecord(side->fork, st));
+      PG_CHECK_CUDA(cudaStreamWaitEvent(side->side, side->fork, 0));
+      ss = side->side;
+    }
+    aggn_small_kernel<T, VB, G><<<blocks, 256, 0, ss>>>(g, x, ldxb, out, ldo, nvec, row_div, acc_rows, da);
+    PG_LAUNCH_CHECK();
+    if (side != nullptr) PG_CHECK_CUDA(cudaEventRecord(side->join, ss));
+  }
+  if (g.n_chunks_long > 0) {
+    const unsigned blocks = static_cast<unsigned>((g.n_chunks_long + 7) / 8);
+    aggn_long_kernel<T, VB, G><<<blocks, 256, 0, st>>>(g, x, ldxb, out, ldo, nvec, row_div, acc_rows, scratch, lds, da);
+    PG_LAUNCH_CHECK();
+  }
+  if (g.n_long > 0) {
+    agg_fixup_kernel<T, VB><<<g.n_long, 256, 0, st>>>(g, out, ldo, nvec, row_div, acc_rows, scratch, lds, da);
+    PG_LAUNCH_CHECK();
+  }
+  if (side != nullptr) PG_CHECK_CUDA(cudaStreamWaitEvent(st, side->join, 0));
+  return PG_OK;
+}
+
 template <typename T, int VB, int VPL>
 static int launch_agg2(const pg_csr& g, const T* x, int64_t ldx, T* out, int64_t ldo, int nvec,
                        const float* row_div, int acc_rows, float* scratch, int64_t lds, const DropArg& da, cudaStream_t st) {
@@ -693,6 +925,11 @@ static int dispatch_agg(const pg_csr& g, const T* x, int64_t ldx, T* out, int64_
     if (nvec <= 32) return launch_agg2<T, VB, 1>(g, x, ldx, out, ldo, nvec, row_div, acc_rows, scratch, lds, da, st);
     if (nvec <= 64) return launch_agg2<T, VB, 2>(g, x, ldx, out, ldo, nvec, row_div, acc_rows, scratch, lds, da, st);
     return launch_agg2<T, VB, 4>(g, x, ldx, out, ldo, nvec, row_div, acc_rows, scratch, lds, da, st);
+  }
+  if (g_agg_impl >= 2 && g.chunks != nullptr && g_agg_narrow) {
+    if (nvec <= 4) return launch_aggn<T, VB, 4>(g, x, ldx, out, ldo, nvec, row_div, acc_rows, scratch, lds, da, st);
+    if (nvec <= 8) return launch_aggn<T, VB, 8>(g, x, ldx, out, ldo, nvec, row_div, acc_rows, scratch, lds, da, st);
+    return launch_aggn<T, VB, 16>(g, x, ldx, out, ldo, nvec, row_div, acc_rows, scratch, lds, da, st);
   }
   if (nvec <= 4) PG_AGG(4, 1);
   if (nvec <= 8) PG_AGG(8, 1);
@@ -791,6 +1028,10 @@ extern "C" int pg_set_option(const char* name, int value) {
   if (strcmp(name, "agg_unroll") == 0) {
     PG_REQUIRE(value == 4 || value == 8, "agg_unroll must be 4 or 8");
     pg::g_agg_unroll = value;
+    return PG_OK;
+  }
+  if (strcmp(name, "agg_narrow") == 0) {
+    pg::g_agg_narrow = value ? 1 : 0;
     return PG_OK;
   }
   if (strcmp(name, "agg_overlap") == 0) {

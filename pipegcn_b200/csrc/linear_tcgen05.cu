@@ -51,6 +51,9 @@ struct GemmArgs {
   uint32_t idesc;
   int is_tf32;
   int tma_store;             // 1: epilogue stages through shared memory and stores with TMA
+  DropArg drop;              // dropout applied to the output as it is written (thresh16 == 0: none)
+  int64_t drop_row0;         // row index of c's first row in the tensor the mask is defined on
+  int drop_nvec;             // 16-byte vectors per row of that tensor
 };
 
 // bias / row scale / convert / store `cnt` (16 or 32) accumulator columns of one row
@@ -200,6 +203,7 @@ linear_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const GemmArgs p) {
     const int q = warp - 4;                                  // == warp % 4: TMEM lane quarter
     int as = 0;
     uint32_t aphase = 0;
+    const uint32_t drop_hi = drop_seed_hi(p.drop);
     if (p.tma_store) {
       // TMEM -> registers -> (bias, row scale, convert) -> 128B-swizzled smem slab -> TMA store:
       // every global write is a full, coalesced 128-byte row segment issued by the copy engine
@@ -230,6 +234,29 @@ linear_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const GemmArgs p) {
               v[i + 1] = (__uint_as_float(r[i + 1]) + b4.y) * scale;
               v[i + 2] = (__uint_as_float(r[i + 2]) + b4.z) * scale;
               v[i + 3] = (__uint_as_float(r[i + 3]) + b4.w) * scale;
+            }
+            if (p.drop.thresh16 != 0u) {
+              // mask of the (rounded) output, per 16-byte vector: what pg_dropout_rows would make of c
+              const uint64_t ibase = static_cast<uint64_t>(p.drop_row0 + row) * p.drop_nvec;
+              if (p.out_bf16) {
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                  float t[8];
+#pragma unroll
+                  for (int j = 0; j < 8; ++j) t[j] = __bfloat162float(__float2bfloat16_rn(v[8 * h + j]));
+                  drop_apply<8>(t, ibase + ((c0 + cc) >> 3) + h, p.drop.thresh16, p.drop.scale, p.drop.seed_lo, drop_hi);
+#pragma unroll
+                  for (int j = 0; j < 8; ++j) v[8 * h + j] = t[j];
+                }
+              } else {
+#pragma unroll
+                for (int h = 0; h < 4; ++h) {
+                  float t[4] = {v[4 * h], v[4 * h + 1], v[4 * h + 2], v[4 * h + 3]};
+                  drop_apply<4>(t, ibase + ((c0 + cc) >> 2) + h, p.drop.thresh16, p.drop.scale, p.drop.seed_lo, drop_hi);
+#pragma unroll
+                  for (int j = 0; j < 4; ++j) v[4 * h + j] = t[j];
+                }
+              }
             }
             if (p.out_bf16) {                                // 16 columns = 2 chunks of 16 bytes
 #pragma unroll
@@ -327,6 +354,12 @@ static int g_sm_count = 0;
 
 extern "C" int pg_linear(int dtype_in, int dtype_out, const pg_gemm_src* srcs, int32_t n_src, const float* bias,
                          const float* row_div, void* c, int64_t ldc, int32_t m, int32_t n, void* stream) {
+  return pg_linear_drop(dtype_in, dtype_out, srcs, n_src, bias, row_div, c, ldc, m, n, nullptr, 0, stream);
+}
+
+extern "C" int pg_linear_drop(int dtype_in, int dtype_out, const pg_gemm_src* srcs, int32_t n_src, const float* bias,
+                              const float* row_div, void* c, int64_t ldc, int32_t m, int32_t n, const pg_drop* drop,
+                              int64_t drop_row0, void* stream) {
   using namespace pg;
   PG_REQUIRE(srcs && c, "pg_linear: null operand");
   PG_REQUIRE(n_src >= 1 && n_src <= kMaxSrc, "pg_linear: 1..%d operand pairs, got %d", kMaxSrc, n_src);
@@ -385,6 +418,10 @@ extern "C" int pg_linear(int dtype_in, int dtype_out, const pg_gemm_src* srcs, i
       maps.c = maps.a[0];
     }
   }
+  p.drop = make_drop(drop);
+  p.drop_row0 = drop_row0;
+  p.drop_nvec = static_cast<int>(round_up(n, p.out_bf16 ? 8 : 4) / (p.out_bf16 ? 8 : 4));
+  PG_REQUIRE(p.drop.thresh16 == 0u || p.tma_store, "pg_linear_drop: the fused dropout needs 16-byte aligned output rows");
   const int n_tiles = (m + kBlockM - 1) / kBlockM;
   const int grid = n_tiles < g_sm_count ? n_tiles : g_sm_count;
   const size_t smem = static_cast<size_t>(kStages) * (kABytes + p.n_pad * kRowBytes) + 4 * kSlabBytes /*staging*/ +

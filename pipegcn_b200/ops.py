@@ -204,9 +204,11 @@ def _halves(t):
     return (t.hi, t.lo) if isinstance(t, Split) else split_tf32(t)
 
 
-def gemm_nt(a0, b0, a1=None, b1=None, bias=None, row_div=None, out=None, out_dtype=None) -> torch.Tensor:
+def gemm_nt(a0, b0, a1=None, b1=None, bias=None, row_div=None, out=None, out_dtype=None, drop=None,
+            drop_row0: int = 0) -> torch.Tensor:
     """out[m, n] = a0 @ b0^T (+ a1 @ b1^T) (+ bias) (/ row_div[:, None]) on the tcgen05 tensor cores.  Operands may be
-    `Split` objects (fp32 operands split once by the caller)."""
+    `Split` objects (fp32 operands split once by the caller).  `drop`: dropout mask applied to `out` as it is written
+    (out's first row is row `drop_row0` of the tensor the mask is defined on)."""
     raw = [(a0, b0)] + ([(a1, b1)] if a1 is not None else [])
     a0, b0 = _plain(a0), _plain(b0)
     pairs = [(_rows(_plain(a)), _rows(_plain(b))) for a, b in raw]
@@ -219,6 +221,7 @@ def gemm_nt(a0, b0, a1=None, b1=None, bias=None, row_div=None, out=None, out_dty
                         None if len(raw) == 1 else _plain(raw[1][1])[i:i + 256],
                         None if bias is None else bias[i:i + 256], row_div, None, out_dtype)
                 for i in range(0, n, 256)]
+        assert drop is None or drop.p == 0, "fused dropout with n > 256 is not supported"
         res = torch.cat(outs, dim=1)
         if out is not None:
             out.copy_(res)
@@ -242,6 +245,13 @@ def gemm_nt(a0, b0, a1=None, b1=None, bias=None, row_div=None, out=None, out_dty
     if bias is not None:
         bias = bias.detach().to(torch.float32).contiguous()
     _C.count()
+    if drop is not None and drop.p > 0:
+        _C.check(_C.lib.pg_linear_drop(_C.dtype_code(a0.dtype), _C.dtype_code(out.dtype), srcs, len(pairs),
+                                       bias.data_ptr() if bias is not None else None,
+                                       row_div.data_ptr() if row_div is not None else None,
+                                       out.data_ptr(), out.stride(0), m, n, C.byref(drop.c()), int(drop_row0),
+                                       _C.stream_ptr()), "pg_linear_drop")
+        return out
     _C.check(_C.lib.pg_linear(_C.dtype_code(a0.dtype), _C.dtype_code(out.dtype), srcs, len(pairs),
                               bias.data_ptr() if bias is not None else None,
                               row_div.data_ptr() if row_div is not None else None,
@@ -426,10 +436,12 @@ class SageLayerNarrowFn(torch.autograd.Function):
         if ctx.needs_input_grad[0]:
             g_feat = alloc_rows(feat.shape[0], feat.shape[1], feat.dtype, feat.device)
             w1t, w2t = padded_weight(w1, feat.dtype, transpose=True), padded_weight(w2, feat.dtype, transpose=True)
-            gemm_nt(dzsp.rows(0, n_in) if is_split else dz[:n_in], w2t, gsp, w1t, out=g_feat[:n_in])
+            db = ctx.drop_bwd if (ctx.drop_bwd is not None and ctx.drop_bwd.p > 0 and feat.shape[1] <= 256
+                                  and _drop_ok(g_feat)) else None   # dropout backward in the GEMM's epilogue
+            gemm_nt(dzsp.rows(0, n_in) if is_split else dz[:n_in], w2t, gsp, w1t, out=g_feat[:n_in], drop=db)
             if feat.shape[0] > n_in:
-                gemm_nt(dzsp.rows(n_in) if is_split else dz[n_in:], w2t, out=g_feat[n_in:])
-            if ctx.drop_bwd is not None and ctx.drop_bwd.p > 0:       # g_feat comes out of a GEMM here: one pass
+                gemm_nt(dzsp.rows(n_in) if is_split else dz[n_in:], w2t, out=g_feat[n_in:], drop=db, drop_row0=n_in)
+            if db is None and ctx.drop_bwd is not None and ctx.drop_bwd.p > 0:
                 dropout_rows(g_feat, ctx.drop_bwd, out=g_feat)
         gw1 = wgrad(gsp, fsp.rows(0, n_in) if is_split else feat[:n_in]).to(w1.dtype)
         gw2 = wgrad(dzsp, fsp).to(w2.dtype)

@@ -2,7 +2,8 @@
 forward (CSR by destination, with the division) and backward (CSC by source, accumulate) for the kernel variants
 (`agg_impl` 1 = row per lane group; 2 = chunked; 3 = chunked with the long rows staged through shared memory by
 cp.async; n/h = without/with L2 eviction hints; 4/5 = CTAs per SM the register-landing long-row kernel is built for;
-trailing s = short-row kernel serialised after the long-row kernel instead of on a side stream),
+trailing s = short-row kernel serialised after the long-row kernel instead of on a side stream, trailing w = rows of
+at most 16 vectors through the row-per-group kernel instead of the chunked sub-warp kernels),
 CUDA-event timed, checked against cuSPARSE (fp32 SpMM); one JSON line per variant.
 
     python tools/agg_bench.py [shape=rmat-1m] [P=1] [dtype=bf16] [d=n_feat] [--once] [--variants 1,2h4,...]
@@ -77,7 +78,8 @@ for var in variants:
     if impl >= 2:
         _C.check(_C.lib.pg_set_option(b"agg_l2_hint", 1 if var[1] == "h" else 0))
         _C.check(_C.lib.pg_set_option(b"agg_occ", int(var[2])))
-        _C.check(_C.lib.pg_set_option(b"agg_overlap", 0 if var.endswith("s") else 1))
+        _C.check(_C.lib.pg_set_option(b"agg_overlap", 0 if "s" in var[3:] else 1))
+        _C.check(_C.lib.pg_set_option(b"agg_narrow", 0 if "w" in var[3:] else 1))
     of = ops.aggregate(graph.fwd, x, row_div=graph.in_deg_f)
     ob = ops.aggregate(graph.bwd, gy, out=torch.zeros_like(gx), acc_rows=0)
     err_f = ((of.float() - ref_f).abs().max() / ref_f.abs().max()).item()
@@ -94,3 +96,4 @@ _C.lib.pg_set_option(b"agg_impl", 2)
 _C.lib.pg_set_option(b"agg_l2_hint", 0)
 _C.lib.pg_set_option(b"agg_occ", 4)
 _C.lib.pg_set_option(b"agg_overlap", 1)
+_C.lib.pg_set_option(b"agg_narrow", 1)
