@@ -182,6 +182,11 @@ int pg_ln_relu_bwd(const void* g_out, int64_t ldg, const void* out, int64_t ldo,
                    const float* mean, const float* rstd, const float* gamma, int relu, void* g_y, int64_t ldgy,
                    float* dgamma, float* dbeta, float* colsum, float* partial, int32_t n_rows, int32_t d,
                    int dtype, void* stream);
+/* the same; with beta given the ReLU mask is recomputed from y (the forward's expression) and `out` is not read */
+int pg_ln_relu_bwd2(const void* g_out, int64_t ldg, const void* out, int64_t ldo, const void* y, int64_t ldy,
+                    const float* mean, const float* rstd, const float* gamma, const float* beta, int relu, void* g_y,
+                    int64_t ldgy, float* dgamma, float* dbeta, float* colsum, float* partial, int32_t n_rows, int32_t d,
+                    int dtype, void* stream);
 /* loss[0] = sum_rows (logsumexp(z) - z[label]) over the first n_rows rows: CrossEntropyLoss(reduction='sum') */
 int pg_ce_fwd(const void* z, int64_t ld, const int64_t* labels, int32_t n_rows, int32_t c, int dtype, float* lse,
               float* partial, float* loss, void* stream);

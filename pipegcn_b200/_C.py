@@ -71,6 +71,8 @@ def _load():
         "pg_ln_relu_fwd": (C.c_int, [vp, i64, vp, vp, f32, C.c_int, vp, i64, vp, vp, i32, i32, C.c_int, vp]),
         "pg_ln_relu_bwd": (C.c_int, [vp, i64, vp, i64, vp, i64, vp, vp, vp, C.c_int, vp, i64, vp, vp, vp, vp, i32, i32,
                                      C.c_int, vp]),
+        "pg_ln_relu_bwd2": (C.c_int, [vp, i64, vp, i64, vp, i64, vp, vp, vp, vp, C.c_int, vp, i64, vp, vp, vp, vp, i32, i32,
+                                      C.c_int, vp]),
         "pg_ce_fwd": (C.c_int, [vp, i64, vp, i32, i32, C.c_int, vp, vp, vp, vp]),
         "pg_ce_bwd": (C.c_int, [vp, i64, vp, vp, vp, i32, i32, i32, C.c_int, vp, i64, vp, vp, vp]),
         "pg_push_rows_per_cta": (C.c_int, []),

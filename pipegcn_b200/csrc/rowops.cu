@@ -105,21 +105,25 @@ __global__ void __launch_bounds__(kRowThreads)
 ln_relu_bwd_kernel(const T* __restrict__ g_out, int64_t ldg, const T* __restrict__ out, int64_t ldo,
                    const T* __restrict__ y, int64_t ldy, const float* __restrict__ mean, const float* __restrict__ rstd,
                    const float* __restrict__ gamma, int relu, T* __restrict__ g_y, int64_t ldgy,
-                   float* __restrict__ partial, int n_rows, int d) {
+                   float* __restrict__ partial, int n_rows, int d, const float* __restrict__ beta) {
   using P = Pack<T, 16>;
   using Raw = typename P::Raw;
   constexpr int V = P::V;
+  // beta given: the ReLU mask is recomputed from y (same expression as the forward) instead of read from `out` --
+  // one [N, d] tensor less to read
+  const bool remask = relu && beta != nullptr;
   extern __shared__ float red[];                             // [3][d]
   const int lane = threadIdx.x & 31;
   const int warps = (gridDim.x * kRowThreads) >> 5;
   const int nvec = d / V;
-  float gm[VPL][V], cg[VPL][V], cb[VPL][V], cy[VPL][V];      // gamma and this lane's column partials
+  float gm[VPL][V], bt[VPL][V], cg[VPL][V], cb[VPL][V], cy[VPL][V];      // gamma, beta and this lane's column partials
 #pragma unroll
   for (int j = 0; j < VPL; ++j)
 #pragma unroll
     for (int i = 0; i < V; ++i) {
       const int c = (lane + j * 32) * V + i;
       gm[j][i] = c < d ? __ldg(gamma + c) : 0.f;
+      bt[j][i] = (remask && c < d) ? __ldg(beta + c) : 0.f;
       cg[j][i] = cb[j][i] = cy[j][i] = 0.f;
     }
 
@@ -133,7 +137,7 @@ ln_relu_bwd_kernel(const T* __restrict__ g_out, int64_t ldg, const T* __restrict
           const int64_t c = static_cast<int64_t>(lane + j * 32) * V;
           rg[r][j] = *reinterpret_cast<const Raw*>(g_out + static_cast<int64_t>(row0 + r) * ldg + c);
           ry[r][j] = *reinterpret_cast<const Raw*>(y + static_cast<int64_t>(row0 + r) * ldy + c);
-          if (relu) ro[r][j] = *reinterpret_cast<const Raw*>(out + static_cast<int64_t>(row0 + r) * ldo + c);
+          if (relu && !remask) ro[r][j] = *reinterpret_cast<const Raw*>(out + static_cast<int64_t>(row0 + r) * ldo + c);
         }
 #pragma unroll
     for (int r = 0; r < R; ++r) {
@@ -148,11 +152,12 @@ ln_relu_bwd_kernel(const T* __restrict__ g_out, int64_t ldg, const T* __restrict
           float g[V], o[V], yy[V];
           P::unpack(rg[r][j], g);
           P::unpack(ry[r][j], yy);
-          if (relu) P::unpack(ro[r][j], o);
+          if (relu && !remask) P::unpack(ro[r][j], o);
 #pragma unroll
           for (int i = 0; i < V; ++i) {
-            const float gg = (relu && !(o[i] > 0.f)) ? 0.f : g[i];
             const float xx = (yy[i] - mu) * rs;
+            const bool dead = remask ? !((yy[i] - mu) * rs * gm[j][i] + bt[j][i] > 0.f) : (relu && !(o[i] > 0.f));
+            const float gg = dead ? 0.f : g[i];
             xh[j][i] = xx;
             gx[j][i] = gg * gm[j][i];
             s1 += gx[j][i];
@@ -375,18 +380,26 @@ extern "C" int pg_ln_relu_bwd(const void* g_out, int64_t ldg, const void* out, i
                               const float* mean, const float* rstd, const float* gamma, int relu, void* g_y,
                               int64_t ldgy, float* dgamma, float* dbeta, float* colsum, float* partial,
                               int32_t n_rows, int32_t d, int dtype, void* stream) {
+  return pg_ln_relu_bwd2(g_out, ldg, out, ldo, y, ldy, mean, rstd, gamma, nullptr, relu, g_y, ldgy, dgamma, dbeta, colsum,
+                         partial, n_rows, d, dtype, stream);
+}
+
+extern "C" int pg_ln_relu_bwd2(const void* g_out, int64_t ldg, const void* out, int64_t ldo, const void* y, int64_t ldy,
+                               const float* mean, const float* rstd, const float* gamma, const float* beta, int relu,
+                               void* g_y, int64_t ldgy, float* dgamma, float* dbeta, float* colsum, float* partial,
+                               int32_t n_rows, int32_t d, int dtype, void* stream) {
   using namespace pg;
   PG_REQUIRE(g_out && y && mean && rstd && gamma && g_y && partial, "pg_ln_relu_bwd: null argument");
-  PG_REQUIRE(!relu || out, "pg_ln_relu_bwd: relu needs the forward output");
+  PG_REQUIRE(!relu || out || beta, "pg_ln_relu_bwd: relu needs the forward output or beta");
   const int es = elem_size(dtype), v = 16 / es;
   PG_REQUIRE(d > 0 && d % v == 0 && d / v <= 32 * kMaxVec, "pg_ln_relu_bwd: unsupported d=%d", d);
   PG_REQUIRE(vec_bytes(g_out, ldg, es) == 16 && vec_bytes(y, ldy, es) == 16 && vec_bytes(g_y, ldgy, es) == 16 &&
-             (!relu || vec_bytes(out, ldo, es) == 16), "pg_ln_relu_bwd: rows must be 16-byte aligned");
+             (!relu || beta || vec_bytes(out, ldo, es) == 16), "pg_ln_relu_bwd: rows must be 16-byte aligned");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int grid = row_grid(n_rows);
   const size_t smem = 3 * static_cast<size_t>(d) * sizeof(float);
   const int vpl = (d / v + 31) / 32;
-#define PG_LNB(T_, VPL_, R_) ln_relu_bwd_kernel<T_, VPL_, R_><<<grid, kRowThreads, smem, st>>>(static_cast<const T_*>(g_out), ldg, static_cast<const T_*>(out), ldo, static_cast<const T_*>(y), ldy, mean, rstd, gamma, relu, static_cast<T_*>(g_y), ldgy, partial, n_rows, d)
+#define PG_LNB(T_, VPL_, R_) ln_relu_bwd_kernel<T_, VPL_, R_><<<grid, kRowThreads, smem, st>>>(static_cast<const T_*>(g_out), ldg, static_cast<const T_*>(out), ldo, static_cast<const T_*>(y), ldy, mean, rstd, gamma, relu, static_cast<T_*>(g_y), ldgy, partial, n_rows, d, beta)
   if (dtype == PG_F32) {
     if (vpl <= 1) PG_LNB(float, 1, 2); else if (vpl <= 2) PG_LNB(float, 2, 1); else PG_LNB(float, 4, 1);
   } else {

@@ -518,14 +518,14 @@ class LayerNormReLU(torch.autograd.Function):
             _C.check(_C.lib.pg_ln_relu_fwd(y.data_ptr(), y.stride(0), g32.data_ptr(), b32.data_ptr(), float(eps), int(relu),
                                            out.data_ptr(), out.stride(0), mean.data_ptr(), rstd.data_ptr(), n, d,
                                            _C.dtype_code(y.dtype), _C.stream_ptr()), "pg_ln_relu_fwd")
-        ctx.save_for_backward(y, clean if clean is not None else out, mean, rstd, g32)
+        ctx.save_for_backward(y, mean, rstd, g32, b32)
         ctx.relu = bool(relu)
         ctx.param_dtype = gamma.dtype
         return out
 
     @staticmethod
     def backward(ctx, g):
-        y, out, mean, rstd, g32 = ctx.saved_tensors
+        y, mean, rstd, g32, b32 = ctx.saved_tensors
         n, d = y.shape
         if g.dtype != y.dtype or g.stride(1) != 1 or (g.stride(0) * g.element_size()) % 16 or g.data_ptr() % 16:
             g = _tma_ready(g.to(y.dtype))
@@ -534,11 +534,12 @@ class LayerNormReLU(torch.autograd.Function):
         partial = torch.empty(grid * 3 * d, dtype=torch.float32, device=y.device)
         red = torch.empty(3, d, dtype=torch.float32, device=y.device)
         _C.count(2)
-        _C.check(_C.lib.pg_ln_relu_bwd(g.data_ptr(), g.stride(0), out.data_ptr(), out.stride(0), y.data_ptr(), y.stride(0),
-                                       mean.data_ptr(), rstd.data_ptr(), g32.data_ptr(), int(ctx.relu),
-                                       g_y.data_ptr(), g_y.stride(0), red[0].data_ptr(), red[1].data_ptr(),
-                                       red[2].data_ptr(), partial.data_ptr(), n, d, _C.dtype_code(y.dtype),
-                                       _C.stream_ptr()), "pg_ln_relu_bwd")
+        # the ReLU mask is recomputed from y (beta given): the forward output is neither kept nor read
+        _C.check(_C.lib.pg_ln_relu_bwd2(g.data_ptr(), g.stride(0), None, 0, y.data_ptr(), y.stride(0),
+                                        mean.data_ptr(), rstd.data_ptr(), g32.data_ptr(), b32.data_ptr(), int(ctx.relu),
+                                        g_y.data_ptr(), g_y.stride(0), red[0].data_ptr(), red[1].data_ptr(),
+                                        red[2].data_ptr(), partial.data_ptr(), n, d, _C.dtype_code(y.dtype),
+                                        _C.stream_ptr()), "pg_ln_relu_bwd")
         _stash_colsum(g_y, red[2])
         return g_y, red[0].to(ctx.param_dtype), red[1].to(ctx.param_dtype), None, None, None, None, None
 

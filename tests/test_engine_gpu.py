@@ -234,6 +234,7 @@ def test_fused_dropout_equals_separate_passes(mode, dtype):
     try:
         for fused in (True, False):
             ops.FUSED_DROPOUT = fused
+            ops._dropout_calls = 0          # layer 0 (static features) keeps the stand-alone pass, keyed by a call counter
             torch.manual_seed(123)
             _, eargs = make_args(g, 16, n_epochs=3, n_hidden=64, dropout=0.5, **MODES[mode])
             eargs.dtype = dtype
