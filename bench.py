@@ -69,6 +69,9 @@ def parse():
     p.add_argument("--dropout", type=float, default=0.5, help="reference default (helper/parser.py:14)")
     p.add_argument("--partition-method", default="random", choices=["random", "metis"])
     p.add_argument("--partition-obj", default="vol", choices=["vol", "cut"])
+    p.add_argument("--graph-device", default="cuda", choices=["cuda", "cpu"],
+                   help="where the synthetic graph is generated (the CPU and CUDA generators give different graphs; a METIS "
+                        "partition cached under partitions/ belongs to the graph of one of them)")
     p.add_argument("--scale-down", type=int, default=1, help="1/k nodes and edges of the named shape (debug, stated in config)")
     p.add_argument("--cpu-full", action="store_true", help="cpu_baseline leg: time the full graph instead of the bounded sample")
     p.add_argument("--no-cpu-baseline", action="store_true")
@@ -285,13 +288,16 @@ def main():
         n_nodes, n_edges, n_feat, n_train = ginfo["n_nodes"], ginfo["n_edges"], spec["n_feat"], ginfo["n_train"]
         part_method = "random (hash of the node id; per-rank construction)"
     else:
-        g = make_graph(spec, device=dev)
+        g = make_graph(spec, device=dev if args.graph_device == "cuda" else "cpu")
+        if args.graph_device == "cpu":
+            g = type(g)(g.n_nodes, g.src.to(dev), g.dst.to(dev), g.feat.to(dev), g.label.to(dev), g.train_mask.to(dev))
         if args.partition_method == "random" or world_size == 1:
             part = random_partition(g.n_nodes, world_size, seed=1, device=dev)
         else:
             from pipegcn_b200.helper.utils import graph_partition
             pargs = argparse.Namespace(partition_method="metis", partition_obj=args.partition_obj, n_partitions=world_size,
-                                       dataset=f"synthetic:{w['shape']}" + (f"-div{args.scale_down}" if args.scale_down > 1 else ""),
+                                       dataset=f"synthetic:{w['shape']}" + (f"-div{args.scale_down}" if args.scale_down > 1 else "")
+                                       + ("-cpugen" if args.graph_device == "cpu" else ""),
                                        graph_name="", inductive=False, partition_cache=True, skip_partition=False)
             part = graph_partition(g, pargs, rank)
         if world_size > 1:   # every rank built the graph itself; make sure they agree
@@ -471,7 +477,8 @@ def main():
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": w["dtype"], "data": "synthetic",
             "config": {"workload": f"{args.workload}: {w['desc']}", "n_nodes": n_nodes, "n_edges": n_edges,
-                       "partitions": world_size, "partition_method": part_method, "dropout": args.dropout,
+                       "partitions": world_size, "partition_method": part_method, "graph_generated_on": args.graph_device,
+                       "dropout": args.dropout,
                        "use_pp": args.use_pp, "scale_down": args.scale_down,
                        "n_in_rank0": layout_info["n_in"], "halo_rank0": layout_info["halo"],
                        "nnz_rank0": layout_info["nnz"], "linear": ops.LINEAR_IMPL,
