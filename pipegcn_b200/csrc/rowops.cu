@@ -82,15 +82,14 @@ ln_relu_fwd_kernel(const T* __restrict__ y, int64_t ldy, const float* __restrict
             o[i] = (relu && v < 0.f) ? 0.f : v;
           }
           Raw packed = P::pack(o);
-          if (out_clean != nullptr) {
-            // the clean result (halo push source, backward), and dropout(result) for the next layer -- computed from
-            // the ROUNDED clean value, i.e. exactly what pg_dropout would make of `out_clean`
+          // the clean result (source of the halo push) when asked for, and dropout(result) for the next layer --
+          // computed from the ROUNDED clean value, i.e. exactly what pg_dropout would make of the clean tensor
+          if (out_clean != nullptr)
             st_vec<16>(out_clean + static_cast<int64_t>(row) * ldc + static_cast<int64_t>(lane + j * 32) * V, packed);
-            if (drop.thresh16 != 0u) {
-              P::unpack(packed, o);
-              drop_apply<V>(o, static_cast<uint64_t>(row) * nvec + (lane + j * 32), drop.thresh16, drop.scale, drop.seed_lo, seed_hi);
-              packed = P::pack(o);
-            }
+          if (drop.thresh16 != 0u) {
+            P::unpack(packed, o);
+            drop_apply<V>(o, static_cast<uint64_t>(row) * nvec + (lane + j * 32), drop.thresh16, drop.scale, drop.seed_lo, seed_hi);
+            packed = P::pack(o);
           }
           st_vec<16>(out + static_cast<int64_t>(row) * ldo + static_cast<int64_t>(lane + j * 32) * V, packed);
         }

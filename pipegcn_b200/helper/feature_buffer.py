@@ -296,6 +296,9 @@ class Buffer(object):
             torch.cuda.current_stream().wait_event(ev)
         return self._f_buf[(layer, v)][:self._num_in, :self._layer_size[layer]]
 
+    def has_peers(self) -> bool:
+        return bool(self._ready and self._peers)
+
     def clean_view(self, layer):
         """[N_in, d] buffer for the CLEAN (not dropped-out) rows of layer `layer` in this epoch's version: with the
         dropout fused into the producers, `inner_view(layer)` holds dropout(h) for the local aggregate / GEMM and this

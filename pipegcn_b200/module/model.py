@@ -74,8 +74,10 @@ class GraphSAGE(GNNBase):
             if isinstance(n, nn.LayerNorm) and self.activation in (F.relu, torch.relu) and ops.ln_relu_supported(h):
                 # LayerNorm + ReLU in one pass, written straight into the next layer's exchange buffer
                 if fuse_drop and dest is not None:
-                    clean = self._buffer().clean_view(i + 1)
-                    if clean is not None and ops._drop_ok(dest) and ops._drop_ok(clean):
+                    buf = self._buffer()
+                    # the clean rows are only needed as the source of the halo push: no peers, no copy
+                    clean = buf.clean_view(i + 1) if buf.has_peers() else None
+                    if ops._drop_ok(dest) and (clean is None or ops._drop_ok(clean)):
                         # ... together with the NEXT layer's dropout: dest <- dropout(h), clean <- h
                         self._fused = (i + 1, clean)
                         return ops.layer_norm_relu(h, n.weight, n.bias, n.eps, relu=True, out=dest, clean=clean,

@@ -508,9 +508,11 @@ class LayerNormReLU(torch.autograd.Function):
         rstd = torch.empty(n, dtype=torch.float32, device=y.device)
         g32, b32 = gamma.detach().float().contiguous(), beta.detach().float().contiguous()
         _C.count()
-        if clean is not None:
+        if clean is not None or drop is not None:
             _C.check(_C.lib.pg_ln_relu_drop_fwd(y.data_ptr(), y.stride(0), g32.data_ptr(), b32.data_ptr(), float(eps),
-                                                int(relu), out.data_ptr(), out.stride(0), clean.data_ptr(), clean.stride(0),
+                                                int(relu), out.data_ptr(), out.stride(0),
+                                                clean.data_ptr() if clean is not None else None,
+                                                clean.stride(0) if clean is not None else 0,
                                                 mean.data_ptr(), rstd.data_ptr(), n, d, _C.dtype_code(y.dtype),
                                                 C.byref(drop.c()) if drop is not None else None, _C.stream_ptr()),
                      "pg_ln_relu_drop_fwd")

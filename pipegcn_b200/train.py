@@ -192,6 +192,32 @@ class RankEngine:
         # set-up work of the reference (precompute runs once, train.py:287-288) and is not recomputed per step
         self.feat[:, :feat.shape[1]].copy_(feat, non_blocking=True)
 
+    # ---- input pipeline: the next epoch's features travel host -> device while this epoch computes
+    def prefetch_features(self, feat_host) -> int:
+        """Start the asynchronous copy of a [N_in, n_feat] pinned host tensor into one of two staging buffers on a copy
+        stream; returns the slot to hand to `commit_features`."""
+        if not hasattr(self, '_stage'):
+            n_feat = feat_host.shape[1]
+            self._stage = [torch.empty(feat_host.shape[0], n_feat, dtype=self.dtype, device=self.device) for _ in range(2)]
+            self._copy_stream = torch.cuda.Stream(device=self.device)
+            self._staged = [torch.cuda.Event(), torch.cuda.Event()]
+            self._consumed = [torch.cuda.Event(), torch.cuda.Event()]
+            self._stage_n = 0
+        slot = self._stage_n % 2
+        self._stage_n += 1
+        with torch.cuda.stream(self._copy_stream):
+            self._copy_stream.wait_event(self._consumed[slot])        # the epoch that last read this slot has taken it
+            self._stage[slot].copy_(feat_host, non_blocking=True)
+            self._staged[slot].record()
+        return slot
+
+    def commit_features(self, slot: int):
+        """Make the staged features of `slot` the input of the coming epoch (device-to-device, on the compute stream)."""
+        cur = torch.cuda.current_stream()
+        cur.wait_event(self._staged[slot])
+        self.set_features(self._stage[slot])
+        self._consumed[slot].record(cur)
+
     def finish_epoch(self, reduce=True):
         """train.py:357-362."""
         self.buffer.next_epoch()

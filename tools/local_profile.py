@@ -20,7 +20,7 @@ w = bench.WORKLOADS["rmat-1m"]
 g = make_graph(w["shape"], device="cuda")
 part = random_partition(g.n_nodes, P, seed=1, device="cuda")
 layouts = build_layouts(g, part, P)
-eargs = bench.engine_args(w, g, SHAPES[w["shape"]]["n_class"], P, 0.5)
+eargs = bench.engine_args(w, g.n_feat, SHAPES[w["shape"]]["n_class"], int(g.train_mask.sum().item()), P, 0.5)
 del g
 trainer = LocalTrainer(layouts, eargs, LocalWorld(P, "cuda"))
 for _ in range(3):
