@@ -180,15 +180,25 @@ wgrad_tcgen05_kernel(const __grid_constant__ WgradMaps maps, const WgradArgs p) 
   }
 }
 
-// out[n, k] = sum over splits of partial[split][n][k], in split order
+// out[n, k] = sum over splits of partial[split][n][k], in split order (eight partials in flight per thread)
 __global__ void __launch_bounds__(256)
 wgrad_reduce_kernel(const float* __restrict__ partial, int splits, int rows_pad, int k_pad, float* __restrict__ out,
                     int64_t ldo, int n, int k) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= n * k) return;
   const int r = idx / k, c = idx % k;
+  const float* p = partial + static_cast<int64_t>(r) * k_pad + c;
+  const int64_t stride = static_cast<int64_t>(rows_pad) * k_pad;
   float s = 0.f;
-  for (int sp = 0; sp < splits; ++sp) s += partial[(static_cast<int64_t>(sp) * rows_pad + r) * k_pad + c];
+  int sp = 0;
+  for (; sp + 8 <= splits; sp += 8) {
+    float t[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) t[u] = __ldcs(p + (sp + u) * stride);
+#pragma unroll
+    for (int u = 0; u < 8; ++u) s += t[u];
+  }
+  for (; sp < splits; ++sp) s += __ldcs(p + sp * stride);
   out[static_cast<int64_t>(r) * ldo + c] = s;
 }
 
@@ -213,7 +223,7 @@ static int make_mn_map(CUtensorMap* map, const void* ptr, int64_t ld, int m, int
 
 static int wgrad_splits(int m, int kb_rows, int sm_count, int* rows_per_split) {
   const int n_kb = (m + kb_rows - 1) / kb_rows;
-  int splits = std::min(sm_count, std::max(1, n_kb / 4));       // at least 4 k-blocks per CTA
+  int splits = std::min(sm_count, std::max(1, n_kb / 8));       // at least 8 k-blocks per CTA
   const int kb_per = (n_kb + splits - 1) / splits;
   splits = (n_kb + kb_per - 1) / kb_per;
   *rows_per_split = kb_per * kb_rows;

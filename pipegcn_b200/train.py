@@ -96,8 +96,10 @@ class RankEngine:
             p.register_hook(reduce_hook(self.reducer, p, name, args.n_train))
         self.loss_fcn = torch.nn.CrossEntropyLoss(reduction='sum')        # train.py:320
         self.use_graph = bool(getattr(args, 'cuda_graph', False))
+        # the reference's optimiser (train.py:321-323); `fused`: torch's single-kernel implementation of the same update
+        # (one launch instead of seven foreach kernels per step -- 0.17 ms of a 3.3 ms step at 8 GPUs)
         self.optimizer = torch.optim.Adam(self.model.parameters(), lr=args.lr, weight_decay=args.weight_decay,
-                                          capturable=self.use_graph)
+                                          capturable=self.use_graph, fused=bool(getattr(args, 'fused_adam', True)))
         self.graphs = None
         self.epoch = 0
         self.last_logits = None
