@@ -317,7 +317,13 @@ class Buffer(object):
         """Write `feat` into the inner rows of every version of layer `layer` (static input features)."""
         d = self._layer_size[layer]
         for v in range(self._nver):
-            self._f_buf[(layer, v)][:self._num_in, :d].copy_(feat)
+            dst = self._f_buf[(layer, v)][:self._num_in, :d]
+            if feat.is_cuda and feat.dtype == dst.dtype:
+                # an SM kernel, not a copy-engine memcpy: a device-to-device memcpy can queue behind a host-to-device
+                # transfer in flight on the same engine (the input pipeline of the end-to-end arm), a kernel cannot
+                torch.mul(feat, 1, out=dst)
+            else:
+                dst.copy_(feat)
 
     # ------------------------------------------------------------------ epoch control
     def next_epoch(self):
