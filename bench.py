@@ -436,11 +436,10 @@ def main():
             barrier()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-            slot = engine.prefetch_features(feat_host)
+            slot = engine.prefetch_features(feat_host, label_host)
             for i in range(n_steps):
-                nxt = engine.prefetch_features(feat_host) if i + 1 < n_steps else None
+                nxt = engine.prefetch_features(feat_host, label_host) if i + 1 < n_steps else None
                 engine.commit_features(slot)
-                engine.labels.copy_(label_host, non_blocking=True)
                 loss = engine.run_epoch()
                 float(loss.item())                       # device -> host read of the step's result
                 slot = nxt

@@ -192,13 +192,18 @@ class RankEngine:
             return
         # --use-pp: `self.feat` is cat(feat, neighbour mean) (train.py:169-189); the raw half is refreshed, the mean is
         # set-up work of the reference (precompute runs once, train.py:287-288) and is not recomputed per step
-        self.feat[:, :feat.shape[1]].copy_(feat, non_blocking=True)
+        dst = self.feat[:, :feat.shape[1]]
+        if feat.is_cuda and feat.dtype == dst.dtype:
+            torch.mul(feat, 1, out=dst)
+        else:
+            dst.copy_(feat, non_blocking=True)
 
     # ---- input pipeline: the next epoch's features travel host -> device while this epoch computes
-    def prefetch_features(self, feat_host) -> int:
-        """Start the asynchronous copy of a [N_in, n_feat] pinned host tensor into one of two staging buffers on a copy
-        stream; returns the slot to hand to `commit_features`."""
+    def prefetch_features(self, feat_host, label_host=None) -> int:
+        """Start the asynchronous copy of a [N_in, n_feat] pinned host tensor (and optionally the train labels) into one
+        of two staging buffers on a copy stream; returns the slot to hand to `commit_features`."""
         if not hasattr(self, '_stage'):
+            self._stage_lab = [torch.empty_like(self.labels) for _ in range(2)]
             n_feat = feat_host.shape[1]
             self._stage = [torch.empty(feat_host.shape[0], n_feat, dtype=self.dtype, device=self.device) for _ in range(2)]
             self._copy_stream = torch.cuda.Stream(device=self.device)
@@ -210,6 +215,9 @@ class RankEngine:
         with torch.cuda.stream(self._copy_stream):
             self._copy_stream.wait_event(self._consumed[slot])        # the epoch that last read this slot has taken it
             self._stage[slot].copy_(feat_host, non_blocking=True)
+            if label_host is not None:
+                self._stage_lab[slot].copy_(label_host, non_blocking=True)
+            self._stage_has_lab = label_host is not None
             self._staged[slot].record()
         return slot
 
@@ -218,6 +226,8 @@ class RankEngine:
         cur = torch.cuda.current_stream()
         cur.wait_event(self._staged[slot])
         self.set_features(self._stage[slot])
+        if getattr(self, '_stage_has_lab', False):
+            torch.add(self._stage_lab[slot], 0, out=self.labels)     # SM kernel (see Buffer.load_inner)
         self._consumed[slot].record(cur)
 
     def finish_epoch(self, reduce=True):
