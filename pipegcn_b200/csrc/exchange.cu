@@ -77,6 +77,11 @@ halo_push_kernel(const pg_msg* __restrict__ msgs, int n_msgs, const T* __restric
     }
   }
 
+  // messages without rows have no CTA of their own: the first CTA of the launch publishes their flags
+  if (blockIdx.x == 0 && static_cast<int>(threadIdx.x) < n_msgs) {
+    const pg_msg& em = msgs[threadIdx.x];
+    if (em.n_rows == 0 && em.flag != nullptr) st_release_sys(em.flag, value);
+  }
   if (msg.flag != nullptr) {
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -253,8 +258,10 @@ extern "C" int pg_halo_push_drop(const pg_msg* msgs, int32_t n_msgs, int32_t n_c
   else if (dtype == PG_BF16) rc = pg::halo_push_t<__nv_bfloat16>(msgs, n_msgs, n_ctas, src, ld_src, d, vb, momentum, one_minus, value, value_dev, da, st);
   else { pg::set_error("pg_halo_push: unknown dtype %d", dtype); return PG_ERR_INVALID; }
   if (rc != PG_OK) return rc;
-  pg::halo_flag_only_kernel<<<(n_msgs + 63) / 64, 64, 0, st>>>(msgs, n_msgs, value, value_dev);
-  PG_LAUNCH_CHECK();
+  if (n_ctas == 0) {      // every message is empty: nobody else publishes the flags
+    pg::halo_flag_only_kernel<<<(n_msgs + 63) / 64, 64, 0, st>>>(msgs, n_msgs, value, value_dev);
+    PG_LAUNCH_CHECK();
+  }
   return PG_OK;
 }
 
