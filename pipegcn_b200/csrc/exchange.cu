@@ -243,7 +243,7 @@ extern "C" int pg_halo_push(const pg_msg* msgs, int32_t n_msgs, int32_t n_ctas, 
 extern "C" int pg_halo_push_drop(const pg_msg* msgs, int32_t n_msgs, int32_t n_ctas, const void* src, int64_t ld_src,
                                  int32_t d, int dtype, float momentum, float one_minus, uint32_t value,
                                  const uint32_t* value_dev, const pg_drop* drop, void* stream) {
-  PG_REQUIRE(msgs && n_msgs > 0, "pg_halo_push: no messages");
+  PG_REQUIRE(msgs && n_msgs > 0 && n_msgs <= pg::kPushThreads, "pg_halo_push: 1..%d messages per launch", pg::kPushThreads);
   PG_REQUIRE(src != nullptr || n_ctas == 0, "pg_halo_push: null source");
   PG_REQUIRE(d > 0 && ld_src >= d, "pg_halo_push: bad sizes");
   cudaStream_t st = static_cast<cudaStream_t>(stream);

@@ -365,7 +365,7 @@ class Buffer(object):
         if ms is None:
             return
         value, value_dev = self._val(offset)
-        _C.count(2)
+        _C.count()
         if drop is not None and drop.p > 0:
             _C.check(_C.lib.pg_halo_push_drop(ms.ptr, ms.n_msgs, ms.n_ctas, src.data_ptr(), src.stride(0), d,
                                               _C.dtype_code(src.dtype), self._corr_momentum, 1 - self._corr_momentum,
@@ -417,7 +417,7 @@ class Buffer(object):
         self._static0_gen += 1
         ms = self._x0_msgs
         if ms is not None:
-            _C.count(2)
+            _C.count()
             _C.check(_C.lib.pg_halo_push(ms.ptr, ms.n_msgs, ms.n_ctas, feat.data_ptr(), feat.stride(0),
                                          self._layer_size[0], _C.dtype_code(feat.dtype), 0.0, 1.0,
                                          self._static0_gen, None, _C.stream_ptr()), "pg_halo_push")
