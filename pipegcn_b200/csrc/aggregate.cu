@@ -547,65 +547,33 @@ agg3_long_kernel(pg_csr g, const T* __restrict__ x, uint32_t ldx_bytes, T* __res
   }
 }
 
-// per-lane inputs of a chunk of short rows: its column ids (lane < n_rows * len), row ids and divisors (lane < n_rows)
-__device__ __forceinline__ void small_chunk_inputs(const pg_csr& g, const int4& c, int lane, const float* __restrict__ row_div,
-                                                   uint32_t& idx, int& row, float& div) {
-  const int n_rows = c.w >> 2, n_e = c.y * n_rows;
-  idx = lane < n_e ? __ldcs(reinterpret_cast<const uint32_t*>(g.pidx) + c.x + lane) : 0u;
-  row = 0;
-  div = 1.f;
-  if (lane < n_rows) {
-    row = __ldg(g.prow + c.z + lane);
-    if (row_div != nullptr) div = __ldg(row_div + row);
-  }
-}
-
-// chunks [n_chunks_long, n_chunks): n_rows whole rows of equal length (<= 32 entries together) per warp.
-// PERSISTENT warps, software-pipelined: while a warp adds the rows of chunk k it has already issued the loads of
-// chunk k + W's column / row ids and of chunk k + 2W's descriptor (W = warps of the grid), so the dependent chain
-// descriptor -> ids -> feature rows of the one-chunk-per-warp version (ncu: long_scoreboard the top stall, DRAM at
-// 43 % on compulsory traffic) is paid once per warp instead of once per chunk.
+// chunks [n_chunks_long, n_chunks): n_rows whole rows of equal length (<= 32 entries together) per warp
 template <typename T, int VB, int VPL, int U, bool HINT>
-__global__ void __launch_bounds__(256, (VPL == 1 ? 3 : (VPL == 2 ? 2 : 1)))
+__global__ void __launch_bounds__(256, (VPL == 1 ? 4 : (VPL == 2 ? 2 : 1)))
 agg2_small_kernel(pg_csr g, const T* __restrict__ x, uint32_t ldx_bytes, T* __restrict__ out, int64_t ldo, int nvec,
                   const float* __restrict__ row_div, int acc_rows, DropArg drop) {
   using A = Agg2<T, VB, VPL, U, HINT>;
   const int lane = threadIdx.x & 31;
-  const int n_small = g.n_chunks - g.n_chunks_long;
-  const int stride = gridDim.x * 8;
-  int k = blockIdx.x * 8 + (threadIdx.x >> 5);
-  if (k >= n_small) return;
-  const int4* __restrict__ chunks = reinterpret_cast<const int4*>(g.chunks) + g.n_chunks_long;
+  const int cid = g.n_chunks_long + blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (cid >= g.n_chunks) return;
+  const int4 c = __ldcs(reinterpret_cast<const int4*>(g.chunks) + cid);
+  const int n_rows = c.w >> 2, len = c.y, n_e = len * n_rows;
+  const uint32_t my_idx = lane < n_e ? __ldcs(reinterpret_cast<const uint32_t*>(g.pidx) + c.x + lane) : 0u;
+  int my_row = 0;
+  float my_inv = 1.f;
+  if (lane < n_rows) {
+    my_row = __ldg(g.prow + c.z + lane);
+    if (row_div != nullptr) my_inv = 1.f / __ldg(row_div + my_row);
+  }
   A a;
   agg2_setup(a, x, ldx_bytes, out, ldo, acc_rows, nvec, drop);
   if (HINT) {
     a.pol_hot = l2_policy_evict_last();
     a.pol_cold = l2_policy_evict_first();
   }
-  const int4 zero4 = make_int4(0, 0, 0, 0);
-  int4 c = __ldcs(chunks + k);
-  int4 cn = k + stride < n_small ? __ldcs(chunks + k + stride) : zero4;
-  uint32_t my_idx;
-  int my_row;
-  float my_div;
-  small_chunk_inputs(g, c, lane, row_div, my_idx, my_row, my_div);
-#pragma unroll 1
-  for (; k < n_small; k += stride) {
-    uint32_t n_idx = 0u;
-    int n_row = 0;
-    float n_div = 1.f;
-    if (k + stride < n_small) small_chunk_inputs(g, cn, lane, row_div, n_idx, n_row, n_div);      // next chunk's ids
-    const int4 cnn = k + 2 * stride < n_small ? __ldcs(chunks + k + 2 * stride) : zero4;          // descriptor after it
-    const float my_inv = 1.f / my_div;
-    for (int c0 = 0; c0 < nvec; c0 += 32 * VPL) {
-      agg2_columns(a, x, c0, lane, nvec);
-      a.small_chunk(my_idx, my_row, my_inv, c.w >> 2, c.y);
-    }
-    c = cn;
-    cn = cnn;
-    my_idx = n_idx;
-    my_row = n_row;
-    my_div = n_div;
+  for (int c0 = 0; c0 < nvec; c0 += 32 * VPL) {
+    agg2_columns(a, x, c0, lane, nvec);
+    a.small_chunk(my_idx, my_row, my_inv, n_rows, len);
   }
 }
 
@@ -813,15 +781,6 @@ static int launch_aggn(const pg_csr& g, const T* x, int64_t ldx, T* out, int64_t
 // The long-row kernel is bound by instruction issue and L2 bandwidth, the short-row kernel by DRAM latency (it
 // touches the cold sources and writes most of the output): they run side by side, the short rows on a side stream
 // forked from and joined to the caller's stream with events (legal inside a CUDA-graph capture).
-static int agg_sm_count() {
-  static int n = 0;
-  if (n == 0) {
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
-      n = 148;
-  }
-  return n;
-}
 struct AggSide { cudaStream_t main; cudaStream_t side; cudaEvent_t fork, join; };
 static AggSide g_agg_side[32];
 static int g_agg_n_side = 0;
@@ -848,9 +807,7 @@ static int launch_agg2h(const pg_csr& g, const T* x, int64_t ldx, T* out, int64_
   const uint32_t ldxb = static_cast<uint32_t>(ldx * sizeof(T));
   AggSide* side = nullptr;
   if (g.n_chunks > g.n_chunks_long) {                     // the short rows first, on the side stream if there is other work
-    // persistent: at most (resident CTAs per SM) x (SMs) CTAs, every warp walks the chunks with that stride
-    const unsigned blocks = static_cast<unsigned>(std::min<int64_t>((g.n_chunks - g.n_chunks_long + 7) / 8,
-                                                                    static_cast<int64_t>(agg_sm_count()) * (VPL == 1 ? 3 : (VPL == 2 ? 2 : 1))));
+    const unsigned blocks = static_cast<unsigned>((g.n_chunks - g.n_chunks_long + 7) / 8);
     cudaStream_t ss = st;
     if (g_agg_overlap && g.n_chunks_long > 0 && (side = agg_side_for(st)) != nullptr) {
       PG_CHECK_CUDA(cudaEventRecord(side->fork, st));
