@@ -100,7 +100,8 @@ lib, EXPORTS = _load()
 for _k, _v in (("agg_unroll", os.environ.get("PG_AGG_UNROLL")), ("agg_pack_short", os.environ.get("PG_AGG_PACK")),
                ("agg_impl", os.environ.get("PG_AGG_IMPL")), ("agg_l2_hint", os.environ.get("PG_AGG_L2_HINT")),
                ("agg_occ", os.environ.get("PG_AGG_OCC")), ("agg_overlap", os.environ.get("PG_AGG_OVERLAP")),
-               ("agg_narrow", os.environ.get("PG_AGG_NARROW"))):
+               ("agg_narrow", os.environ.get("PG_AGG_NARROW")), ("ln_stage", os.environ.get("PG_LN_STAGE")),
+               ("ce_subwarp", os.environ.get("PG_CE_SUBWARP"))):
     if _v:
         lib.pg_set_option(_k.encode(), int(_v))
 

@@ -190,6 +190,7 @@ agg_fixup_kernel(pg_csr g, T* __restrict__ out, int64_t ldo, int nvec, const flo
   }
 }
 
+extern int g_ln_stage, g_ce_subwarp;   // rowops.cu
 int g_agg_narrow = 1;  // pg_set_option("agg_narrow", 0|1): chunked sub-warp kernels for rows of at most 16 vectors
 int g_agg_overlap = 1; // pg_set_option("agg_overlap", 0|1): short-row kernel on a side stream next to the long-row kernel
 int g_agg_impl = 2;     // pg_set_option("agg_impl", 1|2|3): 1 = row-per-group kernel, 2 = chunked kernels (need pg_csr::chunks),
@@ -1054,6 +1055,14 @@ extern "C" int pg_set_option(const char* name, int value) {
   }
   if (strcmp(name, "agg_pack_short") == 0) {
     pg::g_agg_pack_short = value ? 1 : 0;
+    return PG_OK;
+  }
+  if (strcmp(name, "ln_stage") == 0) {
+    pg::g_ln_stage = value ? 1 : 0;
+    return PG_OK;
+  }
+  if (strcmp(name, "ce_subwarp") == 0) {
+    pg::g_ce_subwarp = value ? 1 : 0;
     return PG_OK;
   }
   pg::set_error("pg_set_option: unknown option '%s'", name);

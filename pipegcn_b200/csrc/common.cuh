@@ -137,18 +137,48 @@ __device__ __forceinline__ uint32_t mix32(uint32_t x) {       // lowbias32 final
   x ^= x >> 16; x *= 0x7feb352dU; x ^= x >> 15; x *= 0x846ca68bU; x ^= x >> 16;
   return x;
 }
+// per-kernel key: the seed's high word mixed with the device-side epoch counter, hashed ONCE per thread
 __device__ __forceinline__ uint32_t drop_seed_hi(const DropArg& a) {
-  return a.step_dev != nullptr ? a.seed_hi + 0x632be5abU * (*a.step_dev + static_cast<uint32_t>(a.step_off) + 1u) : a.seed_hi;
+  return mix32(a.step_dev != nullptr ? a.seed_hi + 0x632be5abU * (*a.step_dev + static_cast<uint32_t>(a.step_off) + 1u)
+                                     : a.seed_hi);
+}
+// One full-avalanche hash per 16-byte vector (the key enters BEFORE the mix: masks of different epochs are
+// uncorrelated), then one odd multiply + xor-shift per pair of elements: 23 integer instructions per 8 elements
+// instead of 54 for a full mix per pair.  tools/dropout_hash_quality.py checks keep rate, in-vector, neighbour and
+// cross-epoch correlations of exactly this function.
+__device__ __forceinline__ uint32_t drop_base(uint64_t i, uint32_t seed_lo, uint32_t key) {
+  const uint32_t lo = static_cast<uint32_t>(i), hi = static_cast<uint32_t>(i >> 32);
+  return mix32((lo ^ seed_lo) + (key + hi * 0x9e3779b9U));
+}
+// 2 x 16 random bits for elements (2 * pair, 2 * pair + 1) of the vector
+__device__ __forceinline__ uint32_t drop_bits(uint32_t base, int pair) {
+  constexpr uint32_t kMul[4] = {0x9e3779b1U, 0x85ebca6bU, 0xc2b2ae35U, 0x27d4eb2fU};
+  const uint32_t h = base * kMul[pair & 3];
+  return h ^ (h >> 16);
 }
 template <int V>
 __device__ __forceinline__ void drop_apply(float (&f)[V], uint64_t i, uint32_t thresh16, float scale, uint32_t seed_lo,
-                                           uint32_t seed_hi) {
-  const uint32_t base = mix32(static_cast<uint32_t>(i) ^ seed_lo) ^ mix32(static_cast<uint32_t>(i >> 32) + seed_hi);
+                                           uint32_t key) {
+  const uint32_t base = drop_base(i, seed_lo, key);
 #pragma unroll
   for (int k = 0; k < V; k += 2) {
-    const uint32_t h = mix32(base + 0x9e3779b9U * (k / 2 + 1));
+    const uint32_t h = drop_bits(base, k / 2);
     f[k] = ((h & 0xffffU) >= thresh16) ? f[k] * scale : 0.f;
     if (k + 1 < V) f[k + 1] = ((h >> 16) >= thresh16) ? f[k + 1] * scale : 0.f;
+  }
+}
+// the same function on float2 pairs (packed fp32x2 multiply)
+template <int H>
+__device__ __forceinline__ void drop_apply2(float2 (&f)[H], uint64_t i, uint32_t thresh16, float scale, uint32_t seed_lo,
+                                            uint32_t key) {
+  const uint32_t base = drop_base(i, seed_lo, key);
+  const float2 sc = make_float2(scale, scale);
+#pragma unroll
+  for (int k = 0; k < H; ++k) {
+    const uint32_t h = drop_bits(base, k);
+    const float2 m = __fmul2_rn(f[k], sc);
+    f[k].x = ((h & 0xffffU) >= thresh16) ? m.x : 0.f;
+    f[k].y = ((h >> 16) >= thresh16) ? m.y : 0.f;
   }
 }
 inline DropArg make_drop(const pg_drop* d) {

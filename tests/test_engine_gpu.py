@@ -218,10 +218,11 @@ def test_engine_with_empty_messages(mode):
             assert abs(float(losses[r].item()) - traces[r].losses[e]) <= 1e-4 * abs(traces[r].losses[e]) + 1e-5
 
 
+@pytest.mark.parametrize("p", [0.5, 0.3])
 @pytest.mark.parametrize("dtype", ["fp32", "bf16"])
 @pytest.mark.parametrize("mode", ["sync_corr", "pipeline_corr"])
-def test_fused_dropout_equals_separate_passes(mode, dtype):
-    """--dropout 0.5: the masks applied by the producers (LayerNorm epilogue, halo push with the receiver's key, transposed
+def test_fused_dropout_equals_separate_passes(mode, dtype, p):
+    """--dropout 0.5 / 0.3 (1 / (1 - p) exact or not): the masks applied by the producers (LayerNorm epilogue, halo push with the receiver's key, transposed
     aggregate / GEMM output) are the masks separate [num_all, d] passes would apply under the same keys: logits and
     losses are bit-identical, gradients identical in fp32 (bf16: the fused store rounds once instead of twice)."""
     from pipegcn_b200 import ops
@@ -236,7 +237,7 @@ def test_fused_dropout_equals_separate_passes(mode, dtype):
             ops.FUSED_DROPOUT = fused
             ops._dropout_calls = 0          # layer 0 (static features) keeps the stand-alone pass, keyed by a call counter
             torch.manual_seed(123)
-            _, eargs = make_args(g, 16, n_epochs=3, n_hidden=64, dropout=0.5, **MODES[mode])
+            _, eargs = make_args(g, 16, n_epochs=3, n_hidden=64, dropout=p, **MODES[mode])
             eargs.dtype = dtype
             trainer = LocalTrainer(layouts, eargs, LocalWorld(3, "cuda"))
             ep = []

@@ -110,3 +110,21 @@ def test_evaluation_bookkeeping(tmp_path, monkeypatch):
     assert best.acc == 0.4 and torch.equal(best.state["weight"], w)
     path = best.save(a)
     assert path == "model/g_final.pth.tar" and set(torch.load(path)) == {"weight", "bias"}
+
+
+def test_dropout_mask_function_statistics():
+    """tools/dropout_hash_quality.py restates drop_base / drop_bits of csrc/common.cuh in numpy: the constants must be
+    the kernel's, and the masks must have the right keep rate and no in-vector / neighbour / epoch correlation."""
+    import importlib.util
+    import os
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("dropout_hash_quality", os.path.join(root, "tools", "dropout_hash_quality.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    src = open(os.path.join(root, "pipegcn_b200", "csrc", "common.cuh")).read()
+    kmul = re.search(r"kMul\[4\] = \{([^}]*)\}", src).group(1)
+    assert [int(t.strip().rstrip("U"), 16) for t in kmul.split(",")] == mod.MUL
+    for const in ("0x7feb352dU", "0x846ca68bU", "0x632be5abU", "0x9e3779b9U"):
+        assert const in src
+    mod.main(1 << 19)

@@ -177,12 +177,17 @@ def test_sage_layer_fn_matches_torch():
         assert (a - b).abs().max().item() <= 1e-4 * b.abs().max().item() + 1e-5     # 3xTF32 tensor-core product
 
 
+@pytest.mark.parametrize("stage", [1, 0])
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
-@pytest.mark.parametrize("d", [16, 256, 512])
-def test_layer_norm_relu_matches_torch(dtype, d):
-    from pipegcn_b200 import ops
+@pytest.mark.parametrize("n,d,relu", [(3000, 16, True), (3001, 256, True), (3000, 512, True), (1237, 104, True),
+                                      (1001, 264, False), (513, 1024, True), (7, 256, True), (70001, 256, True)])
+def test_layer_norm_relu_matches_torch(dtype, n, d, relu, stage):
+    """Full / partial last vector, 1 / 2 / 4 vectors per lane, row counts that leave a ragged last group, with the
+    cp.async staging ring (ln_stage 1) and with plain loads (0)."""
+    from pipegcn_b200 import ops, _C
     from pipegcn_b200.graph import alloc_rows
-    n = 3000
+    if d * (4 if dtype == torch.float32 else 2) > 2048:
+        pytest.skip("row wider than 128 vectors")
     torch.manual_seed(d)
     y = alloc_rows(n, d, dtype, DEV)
     y.copy_(torch.randn(n, d, device=DEV) * 2 + 0.5)
@@ -191,13 +196,20 @@ def test_layer_norm_relu_matches_torch(dtype, d):
     go = torch.randn(n, d, device=DEV).to(dtype)
     yq = y.detach().clone().requires_grad_(True)
     assert ops.ln_relu_supported(yq)
-    out = ops.layer_norm_relu(yq, gamma, beta, 1e-5, relu=True)
-    out.backward(go)
+    _C.check(_C.lib.pg_set_option(b"ln_stage", stage))
+    try:
+        out = ops.layer_norm_relu(yq, gamma, beta, 1e-5, relu=relu)
+        out.backward(go)
+        torch.cuda.synchronize()
+    finally:
+        _C.lib.pg_set_option(b"ln_stage", 1)
     got = [out.detach().float(), yq.grad.float(), gamma.grad.clone(), beta.grad.clone()]
     colsum = ops._take_colsum(yq.grad)
     gamma.grad = beta.grad = None
     yr = y.detach().float().clone().requires_grad_(True)
-    ref = torch.relu(torch.nn.functional.layer_norm(yr, (d,), gamma, beta, 1e-5))
+    ref = torch.nn.functional.layer_norm(yr, (d,), gamma, beta, 1e-5)
+    if relu:
+        ref = torch.relu(ref)
     ref.backward(go.float())
     want = [ref.detach(), yr.grad, gamma.grad, beta.grad]
     tol = 1e-4 if dtype == torch.float32 else 2e-2
@@ -207,22 +219,96 @@ def test_layer_norm_relu_matches_torch(dtype, d):
     assert (colsum - got[1].sum(0)).abs().max().item() <= 1e-3 * max(got[1].sum(0).abs().max().item(), 1.0)
 
 
+@pytest.mark.parametrize("p", [0.5, 0.3])
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
-def test_cross_entropy_sum_matches_torch(dtype):
+@pytest.mark.parametrize("n,d", [(2049, 256), (515, 104)])
+def test_layer_norm_fused_dropout_is_dropout_of_the_clean_result(dtype, n, d, p):
+    """pg_ln_relu_drop_fwd writes the clean result and dropout(clean result) in one pass: both must be BIT-identical to
+    the two separate kernels (p = 0.5 takes the shortcut that scales before rounding, p = 0.3 the general path)."""
     from pipegcn_b200 import ops
-    n, n_train, c = 5000, 3211, 41
+    from pipegcn_b200.graph import alloc_rows
+    torch.manual_seed(n)
+    y = alloc_rows(n, d, dtype, DEV)
+    y.copy_(torch.randn(n, d, device=DEV) * 3 - 0.2)
+    gamma, beta = torch.rand(d, device=DEV) + 0.5, torch.randn(d, device=DEV)
+    step = torch.full((1,), 4, dtype=torch.int32, device=DEV)
+    spec = ops.DropSpec(p, 98765, step, 1)
+    out, clean = alloc_rows(n, d, dtype, DEV), alloc_rows(n, d, dtype, DEV)
+    ops.layer_norm_relu(y, gamma, beta, 1e-5, True, out, clean, spec)
+    plain = ops.layer_norm_relu(y, gamma, beta, 1e-5, True)
+    assert torch.equal(clean, plain)
+    assert torch.equal(out, ops.dropout_rows(plain, spec))
+    kept = (out != 0).float().sum().item() / max((plain != 0).float().sum().item(), 1.0)
+    assert abs(kept - (1 - p)) < 0.01
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_layer_norm_backward_mask_from_output_equals_recomputed_mask(dtype):
+    """pg_ln_relu_bwd (ReLU mask read from the forward output) and pg_ln_relu_bwd2 (mask recomputed from y with the
+    forward's own expression) give the same gradient."""
+    import ctypes as C
+    from pipegcn_b200 import ops, _C
+    from pipegcn_b200.graph import alloc_rows
+    n, d = 1501, 256
+    torch.manual_seed(5)
+    y = alloc_rows(n, d, dtype, DEV)
+    y.copy_(torch.randn(n, d, device=DEV))
+    gamma, beta = torch.rand(d, device=DEV) + 0.5, torch.randn(d, device=DEV)
+    out, mean, rstd = alloc_rows(n, d, dtype, DEV), torch.empty(n, device=DEV), torch.empty(n, device=DEV)
+    code, st = _C.dtype_code(dtype), _C.stream_ptr()
+    _C.check(_C.lib.pg_ln_relu_fwd(y.data_ptr(), y.stride(0), gamma.data_ptr(), beta.data_ptr(), 1e-5, 1, out.data_ptr(),
+                                   out.stride(0), mean.data_ptr(), rstd.data_ptr(), n, d, code, st))
+    g = alloc_rows(n, d, dtype, DEV)
+    g.copy_(torch.randn(n, d, device=DEV))
+    res = []
+    for with_beta in (False, True):
+        g_y = alloc_rows(n, d, dtype, DEV)
+        red = torch.empty(3, d, device=DEV)
+        partial = torch.empty(_C.lib.pg_row_grid(n) * 3 * d, device=DEV)
+        if with_beta:
+            _C.check(_C.lib.pg_ln_relu_bwd2(g.data_ptr(), g.stride(0), None, 0, y.data_ptr(), y.stride(0), mean.data_ptr(),
+                                            rstd.data_ptr(), gamma.data_ptr(), beta.data_ptr(), 1, g_y.data_ptr(),
+                                            g_y.stride(0), red[0].data_ptr(), red[1].data_ptr(), red[2].data_ptr(),
+                                            partial.data_ptr(), n, d, code, st))
+        else:
+            _C.check(_C.lib.pg_ln_relu_bwd(g.data_ptr(), g.stride(0), out.data_ptr(), out.stride(0), y.data_ptr(),
+                                           y.stride(0), mean.data_ptr(), rstd.data_ptr(), gamma.data_ptr(), 1,
+                                           g_y.data_ptr(), g_y.stride(0), red[0].data_ptr(), red[1].data_ptr(),
+                                           red[2].data_ptr(), partial.data_ptr(), n, d, code, st))
+        res.append((g_y.clone(), red.clone()))
+    assert torch.equal(res[0][0], res[1][0]) and torch.equal(res[0][1], res[1][1])
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("c,padded", [(41, False), (41, True), (64, True), (7, True), (172, True), (300, True), (1, True)])
+def test_cross_entropy_sum_matches_torch(dtype, c, padded):
+    """padded: rows from alloc_rows (16-byte aligned stride: the sub-warp kernels, 1 .. 32 lanes per row, 1 .. 2 vectors
+    per lane); not padded: a contiguous [n, c] tensor whose rows are not 16-byte aligned (one warp per row)."""
+    from pipegcn_b200 import ops
+    from pipegcn_b200.graph import alloc_rows
+    n, n_train = 5003, 3211
     torch.manual_seed(1)
-    z = (torch.randn(n, c, device=DEV) * 3).to(dtype).requires_grad_(True)
+    src = (torch.randn(n, c, device=DEV) * 3).to(dtype)
+    if padded:
+        z = alloc_rows(n, c, dtype, DEV)
+        z.copy_(src)
+        z.requires_grad_(True)
+    else:
+        z = src.clone().requires_grad_(True)
     labels = torch.randint(0, c, (n_train,), device=DEV)
     loss = ops.cross_entropy_sum(z, labels, n_train)
-    (loss * 0.5).backward()
-    zr = z.detach().float().requires_grad_(True)
+    g = torch.autograd.grad(loss * 0.5, z)[0]               # the tensor the backward produced (padded rows included)
+    zr = src.float().requires_grad_(True)
     ref = torch.nn.functional.cross_entropy(zr[:n_train], labels, reduction="sum")
     (ref * 0.5).backward()
-    assert abs(loss.item() - ref.item()) <= 1e-5 * abs(ref.item())
+    assert abs(loss.item() - ref.item()) <= 1e-5 * abs(ref.item()) + 1e-6
     tol = 1e-5 if dtype == torch.float32 else 1e-2
-    assert (z.grad.float() - zr.grad).abs().max().item() <= tol
-    assert torch.count_nonzero(z.grad[n_train:]) == 0
+    assert (g.float() - zr.grad).abs().max().item() <= tol
+    assert torch.count_nonzero(g[n_train:]) == 0
+    colsum = ops._take_colsum(g)
+    assert colsum is not None
+    want = g.float().sum(0)
+    assert (colsum - want).abs().max().item() <= 1e-4 * max(want.abs().max().item(), 1.0)
 
 
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
