@@ -1058,7 +1058,8 @@ extern "C" int pg_set_option(const char* name, int value) {
     return PG_OK;
   }
   if (strcmp(name, "ln_stage") == 0) {
-    pg::g_ln_stage = value ? 1 : 0;
+    PG_REQUIRE(value >= 0 && value <= 2, "ln_stage must be 0, 1 or 2");
+    pg::g_ln_stage = value;
     return PG_OK;
   }
   if (strcmp(name, "ce_subwarp") == 0) {
