@@ -38,9 +38,13 @@ int pg_abi_version(void);
 const char* pg_last_error(void);
 /* writes sm major*10+minor, SM count and L2 bytes of `device`; needs a GPU */
 int pg_device_info(int device, int* sm_arch, int* sm_count, int64_t* l2_bytes);
-/* tuning knobs (process-wide): "agg_impl" = 1 | 2 (row-per-group or chunked aggregate kernel);
- * "agg_unroll" = 4 | 8 neighbour rows in flight per lane group;
- * "agg_pack_short" = 0 | 1: two short rows per warp (16 lanes x 2 vectors) when the mean row length is < 12 */
+/* tuning knobs (process-wide; the defaults are the measured best, the other values keep earlier code paths selectable):
+ * "agg_impl" = 1 | 2 | 3 (row-per-group, chunked, chunked + cp.async long rows); "agg_unroll" = 4 | 8 neighbour rows in
+ * flight per lane group; "agg_pack_short" = 0 | 1; "agg_occ" = 4 | 5; "agg_overlap" = 0 | 1 (short rows on a side
+ * stream); "agg_narrow" = 0 | 1 (sub-warp kernels for rows of <= 16 vectors); "agg_l2_hint" = 0 | 1;
+ * "ln_stage" = 0 | 1 | 2 (LayerNorm rows through the cp.async ring: never / one vector per lane / always);
+ * "ce_subwarp" = 0 | 1 (several cross-entropy rows per warp); "gemm_epi_batch" = 0 | 1, "gemm_epi_slabs" = 1 | 2
+ * (GEMM epilogue: TMEM loads of a chunk batched, staging slabs per warp).  Unknown names return PG_ERR_INVALID. */
 int pg_set_option(const char* name, int value);
 
 /* ------------------------------------------------------------------------------------------

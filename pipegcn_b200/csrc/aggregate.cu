@@ -191,6 +191,7 @@ agg_fixup_kernel(pg_csr g, T* __restrict__ out, int64_t ldo, int nvec, const flo
 }
 
 extern int g_ln_stage, g_ce_subwarp;   // rowops.cu
+extern int g_gemm_epi_batch, g_gemm_epi_slabs;   // linear_tcgen05.cu
 int g_agg_narrow = 1;  // pg_set_option("agg_narrow", 0|1): chunked sub-warp kernels for rows of at most 16 vectors
 int g_agg_overlap = 1; // pg_set_option("agg_overlap", 0|1): short-row kernel on a side stream next to the long-row kernel
 int g_agg_impl = 2;     // pg_set_option("agg_impl", 1|2|3): 1 = row-per-group kernel, 2 = chunked kernels (need pg_csr::chunks),
@@ -1060,6 +1061,15 @@ extern "C" int pg_set_option(const char* name, int value) {
   if (strcmp(name, "ln_stage") == 0) {
     PG_REQUIRE(value >= 0 && value <= 2, "ln_stage must be 0, 1 or 2");
     pg::g_ln_stage = value;
+    return PG_OK;
+  }
+  if (strcmp(name, "gemm_epi_slabs") == 0) {
+    PG_REQUIRE(value == 1 || value == 2, "gemm_epi_slabs must be 1 or 2");
+    pg::g_gemm_epi_slabs = value;
+    return PG_OK;
+  }
+  if (strcmp(name, "gemm_epi_batch") == 0) {
+    pg::g_gemm_epi_batch = value ? 1 : 0;
     return PG_OK;
   }
   if (strcmp(name, "ce_subwarp") == 0) {

@@ -51,6 +51,8 @@ struct GemmArgs {
   uint32_t idesc;
   int is_tf32;
   int tma_store;             // 1: epilogue stages through shared memory and stores with TMA
+  int epi_batch;             // 1: the epilogue issues all TMEM loads of a 128-byte chunk before waiting
+  int epi_slabs;             // 1 | 2 staging slabs per epilogue warp
   DropArg drop;              // dropout applied to the output as it is written (thresh16 == 0: none)
   int64_t drop_row0;         // row index of c's first row in the tensor the mask is defined on
   int drop_nvec;             // 16-byte vectors per row of that tensor
@@ -105,9 +107,9 @@ linear_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const GemmArgs p) {
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int b_bytes = p.n_pad * kRowBytes;
   const int stage_bytes = kABytes + b_bytes;
-  uint8_t* slabs = smem + kStages * stage_bytes;                          // 4 x 4 KB, 1024-byte aligned
-  float* s_bias = reinterpret_cast<float*>(slabs + 4 * kSlabBytes);       // [256]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(slabs + 4 * kSlabBytes + 1024);
+  uint8_t* slabs = smem + kStages * stage_bytes;                          // 4 warps x 2 x 4 KB, 1024-byte aligned
+  float* s_bias = reinterpret_cast<float*>(slabs + 8 * kSlabBytes);       // [256]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(slabs + 8 * kSlabBytes + 1024);
   uint64_t* full_bar = bars;                    // [kStages]
   uint64_t* empty_bar = bars + kStages;         // [kStages]
   uint64_t* tfull_bar = bars + 2 * kStages;     // [2]
@@ -207,8 +209,10 @@ linear_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const GemmArgs p) {
     if (p.tma_store) {
       // TMEM -> registers -> (bias, row scale, convert) -> 128B-swizzled smem slab -> TMA store:
       // every global write is a full, coalesced 128-byte row segment issued by the copy engine
-      uint8_t* slab = slabs + q * kSlabBytes;
-      const uint32_t slab_u32 = smem_u32(slab);
+      // two staging slabs per warp: the TMA store of a chunk reads one while the next chunk is written to the other
+      // (epi_slabs == 1: one slab, every chunk waits for the previous store to have read it)
+      const int two = p.epi_slabs == 2 ? 1 : 0;
+      uint32_t ck = 0;                                       // chunks issued by this warp
       const int cpc = p.out_bf16 ? 64 : 32;                  // columns per 128-byte chunk
       const int xr = lane & 7;                               // swizzle phase of this thread's row
       for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
@@ -218,22 +222,42 @@ linear_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const GemmArgs p) {
         const int row = row0 + lane;
         const float scale = (p.row_div != nullptr && row < p.m) ? 1.f / __ldg(p.row_div + row) : 1.f;
         const uint32_t tbase = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(as * p.n_pad);
-        uint8_t* my = slab + lane * kRowBytes;
-        for (int c0 = 0; c0 < p.n; c0 += cpc) {
-          if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // slab free again
+        for (int c0 = 0; c0 < p.n; c0 += cpc, ++ck) {
+          uint8_t* slab = slabs + (q * 2 + (two ? (ck & 1u) : 0u)) * kSlabBytes;
+          const uint32_t slab_u32 = smem_u32(slab);
+          uint8_t* my = slab + lane * kRowBytes;
+          // epi_batch: all TMEM loads of the chunk (up to 4 x 16 columns) are issued first and waited for ONCE, in
+          // flight while the previous chunk's TMA store finishes reading the slab; otherwise one load + wait per 16
+          // columns after the slab is free (pg_set_option("gemm_epi_batch", 0|1))
+          const int nsub = (min(cpc, p.n_pad - c0) + 15) >> 4;
+          uint32_t r[4][16];
+          if (p.epi_batch) {
+#pragma unroll
+            for (int sb = 0; sb < 4; ++sb)
+              if (sb < nsub) tmem_ld16(tbase + c0 + 16 * sb, r[sb]);
+          }
+          if (lane == 0) {                                   // the slab about to be written is free again
+            if (two) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+            else asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+          }
           __syncwarp();
-          for (int cc = 0; cc < cpc && c0 + cc < p.n_pad; cc += 16) {
-            uint32_t r[16];
-            tmem_ld16(tbase + c0 + cc, r);
-            tmem_ld_wait();
+          if (p.epi_batch) tmem_ld_wait();
+#pragma unroll
+          for (int sb = 0; sb < 4; ++sb) {
+            if (sb >= nsub) continue;
+            const int cc = 16 * sb;
+            if (!p.epi_batch) {
+              tmem_ld16(tbase + c0 + cc, r[sb]);
+              tmem_ld_wait();
+            }
             float v[16];
 #pragma unroll
             for (int i = 0; i < 16; i += 4) {
               const float4 b4 = *reinterpret_cast<const float4*>(s_bias + c0 + cc + i);
-              v[i] = (__uint_as_float(r[i]) + b4.x) * scale;
-              v[i + 1] = (__uint_as_float(r[i + 1]) + b4.y) * scale;
-              v[i + 2] = (__uint_as_float(r[i + 2]) + b4.z) * scale;
-              v[i + 3] = (__uint_as_float(r[i + 3]) + b4.w) * scale;
+              v[i] = (__uint_as_float(r[sb][i]) + b4.x) * scale;
+              v[i + 1] = (__uint_as_float(r[sb][i + 1]) + b4.y) * scale;
+              v[i + 2] = (__uint_as_float(r[sb][i + 2]) + b4.z) * scale;
+              v[i + 3] = (__uint_as_float(r[sb][i + 3]) + b4.w) * scale;
             }
             if (p.drop.thresh16 != 0u) {
               // mask of the (rounded) output, per 16-byte vector: what pg_dropout_rows would make of c
@@ -279,8 +303,9 @@ linear_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const GemmArgs p) {
           }
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
           __syncwarp();
-          if (lane == 0 && row0 < p.m) {
-            tma_store_2d(&maps.c, slab_u32, c0, row0);
+          if (lane == 0) {
+            if (row0 < p.m) tma_store_2d(&maps.c, slab_u32, c0, row0);
+            // one group per chunk, empty or not: the slab parity (ck & 1) and the group count stay in step
             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
           }
         }
@@ -349,6 +374,8 @@ static int make_map(CUtensorMap* map, const void* ptr, int64_t ld, int rows, int
 }
 
 static int g_sm_count = 0;
+int g_gemm_epi_batch = 1;     // pg_set_option("gemm_epi_batch", 0|1)
+int g_gemm_epi_slabs = 2;     // pg_set_option("gemm_epi_slabs", 1|2)
 
 }  // namespace pg
 
@@ -404,6 +431,8 @@ extern "C" int pg_linear_drop(int dtype_in, int dtype_out, const pg_gemm_src* sr
     // TMA-store epilogue when the output rows are 16-byte aligned (always true for engine buffers)
     const int eso = p.out_bf16 ? 2 : 4;
     p.tma_store = ((reinterpret_cast<uintptr_t>(c) & 15) == 0 && (ldc * eso) % 16 == 0) ? 1 : 0;
+    p.epi_batch = g_gemm_epi_batch;
+    p.epi_slabs = g_gemm_epi_slabs;
     if (p.tma_store) {
       EncodeTiledFn enc = get_encode();
       cuuint64_t gdim[2] = {static_cast<cuuint64_t>(n), static_cast<cuuint64_t>(m)};
@@ -424,7 +453,7 @@ extern "C" int pg_linear_drop(int dtype_in, int dtype_out, const pg_gemm_src* sr
   PG_REQUIRE(p.drop.thresh16 == 0u || p.tma_store, "pg_linear_drop: the fused dropout needs 16-byte aligned output rows");
   const int n_tiles = (m + kBlockM - 1) / kBlockM;
   const int grid = n_tiles < g_sm_count ? n_tiles : g_sm_count;
-  const size_t smem = static_cast<size_t>(kStages) * (kABytes + p.n_pad * kRowBytes) + 4 * kSlabBytes /*staging*/ +
+  const size_t smem = static_cast<size_t>(kStages) * (kABytes + p.n_pad * kRowBytes) + 8 * kSlabBytes /*staging*/ +
                       1024 /*bias*/ + 256 /*barriers*/ + 1024 /*align*/;
   static bool attr_set = false;       // once: opt in to the full 227 KB of shared memory (not a stream operation)
   if (!attr_set) {

@@ -410,11 +410,30 @@ class SageLayerNarrowFn(torch.autograd.Function):
             feat = feat.contiguous()
         n_in = graph.num_in
         fsp = presplit(feat)                   # fp32: one split of feat for both products
-        z = gemm_nt(fsp, padded_weight(w2, feat.dtype))
         bias = None
         if b1 is not None:
             bias = b1.detach().float() + b2.detach().float()
-        out = gemm_nt(fsp.rows(0, n_in) if isinstance(fsp, Split) else feat[:n_in], padded_weight(w1, feat.dtype), bias=bias)
+        na, nb = w2.shape[0], w1.shape[0]
+        v = 16 // feat.element_size()
+        na_pad = -(-na // v) * v
+        if MERGE_NARROW and na_pad + nb <= 256:
+            # ONE product reads feat once: [z | self part] = feat @ [W2 ; W1]^T (+ [0 | b1 + b2]); the self part of
+            # the halo rows is computed and never read.  W1 starts at a 16-byte aligned column.
+            wc = alloc_rows(na_pad + nb, feat.shape[1], feat.dtype, feat.device)
+            if na_pad != na:
+                wc[na:na_pad].zero_()
+            wc[:na].copy_(w2.detach())
+            wc[na_pad:].copy_(w1.detach())
+            bias_c = None
+            if bias is not None:
+                bias_c = torch.zeros(na_pad + nb, dtype=torch.float32, device=feat.device)
+                bias_c[na_pad:].copy_(bias)
+            zc = gemm_nt(fsp, wc, bias=bias_c)
+            z, out = zc[:, :na], zc[:n_in, na_pad:]
+        else:
+            z = gemm_nt(fsp, padded_weight(w2, feat.dtype))
+            out = gemm_nt(fsp.rows(0, n_in) if isinstance(fsp, Split) else feat[:n_in], padded_weight(w1, feat.dtype),
+                          bias=bias)
         aggregate(graph.fwd, z, out=out, row_div=deg_f, acc_rows=n_in)
         ctx.graph, ctx.deg_f = graph, deg_f
         ctx.has_bias = b1 is not None
@@ -451,6 +470,8 @@ class SageLayerNarrowFn(torch.autograd.Function):
 
 # transform-first when the layer narrows (PG_NARROW=0 keeps the reference's aggregate-first association everywhere)
 NARROW = os.environ.get("PG_NARROW", "1") != "0"
+# ... with the neighbour and self products of its forward in one GEMM (PG_MERGE_NARROW=0: two GEMMs)
+MERGE_NARROW = os.environ.get("PG_MERGE_NARROW", "1") != "0"
 
 
 def sage_layer(feat, graph, deg_f, w1, b1, w2, b2, drop_bwd=None) -> torch.Tensor:
