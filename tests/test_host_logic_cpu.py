@@ -128,3 +128,44 @@ def test_dropout_mask_function_statistics():
     for const in ("0x7feb352dU", "0x846ca68bU", "0x632be5abU", "0x9e3779b9U"):
         assert const in src
     mod.main(1 << 19)
+
+
+def test_multi_value_warp_reduction_network():
+    """csrc/rowops.cu: warp_sum_multi<K> folds K per-lane values with a halving butterfly (a lane keeps the half of the
+    values its own lane bit selects and ships the other half), then broadcasts: every lane must end up with all K
+    totals.  Restated on 32 numpy "lanes" with integer values (exact)."""
+    import numpy as np
+    rng = np.random.default_rng(0)
+    lanes = np.arange(32)
+
+    def shfl_xor(v, o):
+        return v[lanes ^ o]
+
+    for K in (1, 2, 4):
+        v = [rng.integers(-1000, 1000, size=32) for _ in range(K)]
+        want = [int(x.sum()) for x in v]
+        if K == 1:
+            t = v[0].copy()
+            for o in (16, 8, 4, 2, 1):
+                t = t + shfl_xor(t, o)
+            got = [t]
+        elif K == 2:
+            up = (lanes & 16) != 0
+            keep, send = np.where(up, v[1], v[0]), np.where(up, v[0], v[1])
+            t = keep + shfl_xor(send, 16)
+            for o in (8, 4, 2, 1):
+                t = t + shfl_xor(t, o)
+            got = [np.full(32, t[0]), np.full(32, t[16])]
+        else:
+            up = (lanes & 16) != 0
+            k0, k1 = np.where(up, v[2], v[0]), np.where(up, v[3], v[1])
+            s0, s1 = np.where(up, v[0], v[2]), np.where(up, v[1], v[3])
+            a0, a1 = k0 + shfl_xor(s0, 16), k1 + shfl_xor(s1, 16)
+            up2 = (lanes & 8) != 0
+            keep, send = np.where(up2, a1, a0), np.where(up2, a0, a1)
+            t = keep + shfl_xor(send, 8)
+            for o in (4, 2, 1):
+                t = t + shfl_xor(t, o)
+            got = [np.full(32, t[src]) for src in (0, 8, 16, 24)]
+        for k in range(K):
+            assert np.all(got[k] == want[k]), (K, k)
